@@ -1,0 +1,181 @@
+/*
+ * b200rl.h -- C ABI of libb200rl.so: the B200-native (sm_100a) implementation of rllab's
+ * data-parallel hot path (lock-step lane rollout, process_samples, VPG / TRPO update).
+ *
+ * The reference (rll/rllab @ ba78e4c) has NO native boundary on this path: the path is pure Python over
+ * Theano-compiled functions, pybox2d (SWIG) and libmujoco131 (ctypes, rllab/mujoco_py/mjlib.py:17-60).
+ * Each entry point below therefore cites the reference *Python* interface it replaces; the ctypes stub a
+ * maintainer adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B200RL_E* code otherwise; b200rl_last_error() returns
+ *     a thread-local human-readable message for the last failure.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every buffer, the
+ *     library borrows them until the work queued on `stream` completes; no allocation inside hot calls.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are asynchronous.
+ *   - lane layout (structure of arrays, time-major): obs [O][T][N], act/mean [A][T][N], rew/adv/ret/base
+ *     [T][N] float32, flags [T][N] uint8 (bit0 = env done, bit1 = last sample of its path), tstep [T][N]
+ *     uint16 (index of the sample inside its path).  N = lanes on this GPU, T = steps per lane.
+ *   - flat policy parameter layout (rllab core/lasagne_powered.py:16-20): [W0 (O,h1) row-major, b0, W1 (h1,h2),
+ *     b1, Wout (h2,A), bout, log_std (A)];  P = O*h1+h1 + h1*h2+h2 + h2*A+A + A.  Master copy float64,
+ *     kernels read a float32 shadow.
+ *   - reductions are two-stage and order-deterministic: per-block float64 partials in `ws`, then a fixed-order
+ *     finalize; results are SUMS over this GPU's samples already multiplied by the `scale` argument
+ *     (pass 1/B_global so that an NCCL all-reduce(sum) over ranks yields the global mean).
+ */
+#ifndef B200RL_H_
+#define B200RL_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RL_VERSION 100
+
+#define B200RL_OK 0
+#define B200RL_EINVAL (-1)       /* bad argument / unsupported shape */
+#define B200RL_ECUDA (-2)        /* CUDA runtime error (message has the cudaError string) */
+#define B200RL_EUNSUPPORTED (-3) /* env kind / network size not compiled in */
+
+/* env kinds (reference classes): examples/point_env.py, rllab/envs/box2d/cartpole_env.py,
+ * GymEnv("Pendulum-v0") (rllab/envs/gym_env.py), rllab/envs/mujoco/swimmer_env.py, hopper_env.py;
+ * every kind includes the NormalizedEnv action map of rllab/envs/normalized_env.py:78-92. */
+#define B200RL_ENV_POINT 0
+#define B200RL_ENV_CARTPOLE 1
+#define B200RL_ENV_PENDULUM 2
+#define B200RL_ENV_SWIMMER 3
+#define B200RL_ENV_HOPPER 4
+
+#define B200RL_NOISE_UNIFORM 0
+#define B200RL_NOISE_NORMAL 1
+
+#define B200RL_LOSS_TRPO 0 /* -mean(exp(logp_new-logp_old)*adv)   rllab/algos/npo.py:72-82 */
+#define B200RL_LOSS_VPG 1  /* -mean(logp*adv)                     rllab/algos/vpg.py:91     */
+
+#define B200RL_FLAG_DONE 1
+#define B200RL_FLAG_END 2
+
+/* number of float64 slots in the process_samples statistics block (see b200rl_process_samples) */
+#define B200RL_PS_NSUM 16
+#define B200RL_PS_NMAX 4
+
+const char* b200rl_last_error(void);
+int b200rl_version(void);
+/* SM count of the current device (grid sizing helper for callers that size workspaces). */
+int b200rl_device_sms(int* sms_out);
+
+/* Static description of an env kind.  lb/ub: wrapped action bounds (host arrays of act_dim floats) --
+ * Env.action_space / observation_space of rllab/envs/base.py:43-62. */
+int b200rl_env_info(int env_kind, int* obs_dim, int* act_dim, int* state_dim, int* reset_dim, int* noise_kind,
+                    float* lb_host, float* ub_host);
+
+/* Number of policy parameters P for (O, h1, h2, A); <0 if the network size is not compiled in. */
+long long b200rl_policy_num_params(int obs_dim, int h1, int h2, int act_dim);
+
+/* Counter-based Philox4x32-10 noise, the generator the fused rollout uses internally:
+ * out[row][k][n] for row in [row0,row0+rows), k < K, n < N;  value = f(seed, iter, stream_id, lane0+n, row, k).
+ * stream_id 0 = action noise eps (normal), 1 = reset noise (kind of the env).  Replaces the np.random draws of
+ * gaussian_mlp_policy.py:128,135 and of the envs' reset(). */
+int b200rl_fill_noise(float* out, int rows, int row0, int K, int N, long long lane0, int noise_kind,
+                      unsigned int seed, unsigned int iter, int stream_id, void* stream);
+
+/* Env.reset for N lanes (rllab/envs/base.py:26-33; vec_env_executor.py:28-31).  reset_raw [K][N] raw noise or NULL
+ * (then Philox(seed, iter, stream 1, row)).  Writes state [S][N] and obs [O][N]. */
+int b200rl_env_reset(int env_kind, int N, float* state, float* obs_out, const float* reset_raw,
+                     unsigned int seed, unsigned int iter, int row, long long lane0, void* stream);
+
+/* Env.step for N lanes (rllab/envs/base.py:6-24 through NormalizedEnv.step, normalized_env.py:78-92).
+ * actions [A][N] are the policy's raw actions.  Writes obs_out [O][N], rew_out [N], done_out [N]; state is
+ * advanced in place (no auto-reset here: the caller decides, as vec_env_executor.py:14-26 does). */
+int b200rl_env_step(int env_kind, int N, float* state, const float* actions, float* obs_out, float* rew_out,
+                    unsigned char* done_out, void* stream);
+
+/* GaussianMLPPolicy.get_actions (rllab/policies/gaussian_mlp_policy.py:132-137): obs [O][n] ->
+ * act_out, mean_out [A][n], log_std_out [A] (after the min_std clamp).  eps [A][n] or NULL (Philox). */
+int b200rl_policy_get_actions(const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std,
+                              const float* obs, long long n, const float* eps, unsigned int seed, unsigned int iter,
+                              int row, long long lane0, float* act_out, float* mean_out, float* log_std_out,
+                              void* stream);
+
+/* Fused rollout: T lock-step steps of N lanes = BatchSampler.obtain_samples (rllab/algos/batch_polopt.py:22-34)
+ * -> rollout (rllab/sampler/utils.py:6-43) with the vectorized auto-reset semantics of
+ * sandbox/rocky/tf/envs/vec_env_executor.py:14-26.  eps [T][A][N] / reset_raw [T+1][K][N] inject noise (tests),
+ * NULL = in-kernel Philox.  log_std_out [A]. */
+int b200rl_rollout(int env_kind, const float* params_f32, int h1, int h2, float min_std, int N, int T,
+                   int max_path_length, const float* eps, const float* reset_raw, unsigned int seed,
+                   unsigned int iter, long long lane0, float* obs, float* act, float* mean, float* rew,
+                   unsigned char* flags, unsigned short* tstep, float* log_std_out, void* stream);
+
+/* BaseSampler.process_samples numeric core (rllab/sampler/base.py:48-93): LinearFeatureBaseline.predict
+ * (linear_feature_baseline.py:19-23,40-43) with weights w [2O+4] float64 (NULL = zeros), GAE advantages and
+ * discounted returns (special.discount_cumsum), plus the reductions behind the tabular statistics.
+ * sums_out [B200RL_PS_NSUM] float64 (all-reduce SUM across ranks):
+ *   0 sum adv, 1 sum adv^2, 2 count B, 3 n_paths, 4 sum ret@path start, 5 sum undisc. return, 6 sum undisc^2,
+ *   7 sum ret, 8 sum ret^2, 9 sum base, 10 sum base^2, 11 sum (ret-base), 12 sum (ret-base)^2
+ * maxs_out [B200RL_PS_NMAX] float64 (all-reduce MAX): 0 max undisc, 1 -min undisc, 2 -min adv, 3 max adv
+ * ws: float64 workspace of at least b200rl_ws_doubles() entries. */
+int b200rl_process_samples(int obs_dim, int N, int T, const float* obs, const float* rew, const unsigned char* flags,
+                           const unsigned short* tstep, const double* w, double discount, double gae_lambda,
+                           float* adv, float* ret, float* base, double* sums_out, double* maxs_out, double* ws,
+                           void* stream);
+
+/* center_advantages / shift_advantages_to_positive (rllab/algos/util.py:7-12) in place over B samples, from the
+ * (already all-reduced) sums/maxs of b200rl_process_samples. */
+int b200rl_center_advantages(float* adv, long long B, const double* sums, const double* maxs, int center,
+                             int positive, void* stream);
+
+/* LinearFeatureBaseline.fit normal equations (linear_feature_baseline.py:26-33): with d = 2O+4 and
+ * f = [features, ret], writes gram_out [(d+1)*(d+2)/2] float64 = upper triangle (row-major, i<=j) of sum f f^T
+ * over this GPU's samples.  The d x d solve (np.linalg.lstsq on d<=44 unknowns) is done by the caller. */
+int b200rl_lfb_gram(int obs_dim, long long B, const float* obs, const unsigned short* tstep, const float* ret,
+                    double* gram_out, double* ws, void* stream);
+
+/* Surrogate loss and KL(old||new) (npo.py:72-82, vpg.py:91-99, diagonal_gaussian.py:14-34,58-69):
+ * out[0] = scale * sum(-w*adv) (w = likelihood ratio for TRPO, logp for VPG), out[1] = scale * sum(kl),
+ * out[2] = max(kl).  old_log_std [A] (state-independent ParamLayer, lasagne_layers.py:9-30). */
+int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std,
+                   long long B, const float* obs, const float* act, const float* adv, const float* old_mean,
+                   const float* old_log_std, double scale, double* out, double* ws, void* stream);
+
+/* Flat gradient of the surrogate (theano.grad in conjugate_gradient_optimizer.py:184-186 /
+ * first_order_optimizer.py:62-64): g_out [P] float64 = scale * sum over samples. */
+int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std,
+                long long B, const float* obs, const float* act, const float* adv, const float* old_mean,
+                const float* old_log_std, double scale, double* g_out, double* ws, void* stream);
+
+/* Fisher/Hessian-vector product of mean KL at theta_old (PerlmutterHvp, conjugate_gradient_optimizer.py:22-55):
+ * Hx_out [P] = scale * sum_samples J^T M J x  (+ reg_coeff*x and the log_std block added once: pass
+ * add_diag=1 on exactly one rank, or on all ranks with diag_scale = 1/world_size). */
+int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std, long long B,
+               const float* obs, const double* x, double scale, double reg_coeff, double diag_scale, double* Hx_out,
+               double* ws, void* stream);
+
+/* Workspace size (float64 entries) sufficient for every reduction above on the current device. */
+long long b200rl_ws_doubles(void);
+
+/* ---- P-vector kernels (float64, single block; krylov.cg rllab/misc/krylov.py:7-39 and the step/line-search
+ * arithmetic of conjugate_gradient_optimizer.py:258-293; lasagne.updates.adam for VPG) ---- */
+
+/* cg_state [4] float64: 0 rdotr, 1 frozen flag (rdotr < tol seen), 2 last p.z, 3 iterations done */
+int b200rl_cg_init(long long P, const double* g, double* x, double* r, double* p, double* cg_state, void* stream);
+int b200rl_cg_step(long long P, const double* z, double* x, double* r, double* p, double* cg_state,
+                   double residual_tol, void* stream);
+/* step_out [P] = beta * x with beta = sqrt(2*delta/(x.Hx + 1e-8)) (NaN -> 1); info_out[0] = beta */
+int b200rl_trpo_step_size(long long P, const double* x, const double* Hx, double max_constraint_val,
+                          double* step_out, double* info_out, void* stream);
+/* theta_out = theta_prev - ratio * step (float64 master) and its float32 shadow */
+int b200rl_axpy_params(long long P, const double* theta_prev, const double* step, double ratio, double* theta_out,
+                       float* theta_f32_out, void* stream);
+/* lasagne.updates.adam: t is the 1-based step index AFTER increment (first_order_optimizer.py:21-22,62-65) */
+int b200rl_adam_step(long long P, double* theta, float* theta_f32, const double* g, double* m, double* v,
+                     long long t, double lr, double b1, double b2, double eps, void* stream);
+int b200rl_f64_to_f32(long long n, const double* src, float* dst, void* stream);
+
+/* (T,N)-planar lane layout <-> the reference's sample-major (B, dim) float64 wire format
+ * (samples_data["observations"] etc., rllab/sampler/base.py:74-104): dst[(t*N+n)*dim + k] = src[k][t][n]. */
+int b200rl_planes_to_rows_f64(int dim, long long B, const float* src, double* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H_ */

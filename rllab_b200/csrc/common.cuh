@@ -1,0 +1,142 @@
+// Shared device/host helpers for libb200rl (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200rl.h"
+
+namespace b200rl {
+
+// ---------------------------------------------------------------- error handling (C ABI: status + message)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define B200RL_CUDA_CHECK(expr)                                   \
+  do {                                                            \
+    cudaError_t _e = (expr);                                      \
+    if (_e != cudaSuccess) return ::b200rl::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define B200RL_LAUNCH_CHECK(name)                                 \
+  do {                                                            \
+    cudaError_t _e = cudaGetLastError();                          \
+    if (_e != cudaSuccess) return ::b200rl::cuda_fail(_e, name);  \
+  } while (0)
+
+#define B200RL_REQUIRE(cond, ...)       \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::b200rl::set_error(__VA_ARGS__); \
+      return B200RL_EINVAL;             \
+    }                                   \
+  } while (0)
+
+int num_sms();
+
+// partial-reduction workspace geometry: every reduction kernel uses at most MAX_PARTIAL_BLOCKS blocks and
+// writes [block][K] float64 partials; K <= MAX_PARTIAL_K.
+constexpr int MAX_PARTIAL_BLOCKS = 148 * 8;
+constexpr int MAX_PARTIAL_K = 8192;
+
+// ---------------------------------------------------------------- Philox4x32-10 (Salmon et al. 2011)
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __host__ __device__ static inline void round(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(M0, c[0]), hi1 = __umulhi(M1, c[2]);
+#else
+    uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c[0]) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c[2]) >> 32);
+#endif
+    uint32_t lo0 = M0 * c[0], lo1 = M1 * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __host__ __device__ static inline void gen(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                             uint32_t k1, uint32_t out[4]) {
+    uint32_t c[4] = {c0, c1, c2, c3};
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      round(c, k0, k1);
+      k0 += W0;
+      k1 += W1;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+  }
+};
+
+// counter = (lane, row | stream<<28, chunk, lane>>32), key = (seed, iter).  Four floats per call.
+// uniform: (x>>8) * 2^-24 in [0,1);  normal: Box-Muller on ((x>>8)+0.5)*2^-24 in (0,1).
+__device__ inline void noise4(int kind, uint32_t seed, uint32_t iter, int stream_id, long long lane, int row,
+                              int chunk, float out[4]) {
+  uint32_t r[4];
+  Philox::gen((uint32_t)lane, (uint32_t)row | ((uint32_t)stream_id << 28), (uint32_t)chunk,
+              (uint32_t)((unsigned long long)lane >> 32), seed, iter, r);
+  const float s = 1.0f / 16777216.0f;
+  if (kind == B200RL_NOISE_UNIFORM) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = (float)(r[i] >> 8) * s;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+      float u1 = ((float)(r[i] >> 8) + 0.5f) * s;
+      float u2 = ((float)(r[i + 1] >> 8) + 0.5f) * s;
+      float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      out[i] = rad * cs;
+      out[i + 1] = rad * sn;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- math
+// tanh used by every kernel (rollout and update MUST share it so that the likelihood ratio is exactly 1 at
+// theta_old).  |x| < 0.55: odd minimax polynomial; else 1 - 2/(exp(2|x|)+1).  ~1-2 ulp.
+__device__ __forceinline__ float tanh_f(float x) { return tanhf(x); }
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of K per-thread doubles; result valid in thread 0..K-1? -> written to out[k] by thread 0.
+// scratch: K * 32 doubles of shared memory.  Fixed order -> deterministic.
+template <int K, bool IS_MAX = false>
+__device__ inline void block_reduce_store(const double (&v)[K], double* scratch, double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double s = IS_MAX ? warp_max(v[k]) : warp_sum(v[k]);
+    if (lane == 0) scratch[k * 32 + warp] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double s = lane < nwarp ? scratch[k * 32 + lane] : (IS_MAX ? -1.0e300 : 0.0);
+      s = IS_MAX ? warp_max(s) : warp_sum(s);
+      if (lane == 0) out[k] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// finalize: out[k] = post(sum_b partial[b][k]) in fixed block order; one thread per k.
+int launch_finalize_sum(const double* partial, int nblocks, int K, double* out, double scale, cudaStream_t s);
+int launch_finalize_max(const double* partial, int nblocks, int K, double* out, cudaStream_t s);
+
+}  // namespace b200rl

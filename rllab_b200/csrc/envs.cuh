@@ -1,0 +1,134 @@
+// Per-lane environment dynamics (device functions, state in registers).  Each env is a struct with
+//   O, A, S (state floats), K (raw reset noise count), NOISE (uniform|normal), lb()/ub()
+//   reset(s, raw) ; obs(s, o) ; step(s, u, r, done)   with u = action after NormalizedEnv scaling.
+// Reference classes are cited per struct; the NormalizedEnv action map lives in scale_action().
+#pragma once
+#include "common.cuh"
+
+namespace b200rl {
+
+// NormalizedEnv.step (rllab/envs/normalized_env.py:81-83): clip(lb + (a+1)*0.5*(ub-lb), lb, ub).
+// Written with explicit round-to-nearest ops (no FMA contraction) so that it is bit-identical to NumPy float32.
+__device__ __forceinline__ float scale_action(float a, float lb, float ub) {
+  float t = __fmul_rn(__fmul_rn(__fadd_rn(a, 1.0f), 0.5f), __fsub_rn(ub, lb));
+  float s = __fadd_rn(lb, t);
+  return fminf(fmaxf(s, lb), ub);
+}
+
+// ---------------------------------------------------------------- examples/point_env.py:16-27
+struct PointEnvD {
+  static constexpr int KIND = B200RL_ENV_POINT, O = 2, A = 2, S = 2, K = 2, NOISE = B200RL_NOISE_UNIFORM;
+  __host__ __device__ static constexpr float lb(int) { return -0.1f; }
+  __host__ __device__ static constexpr float ub(int) { return 0.1f; }
+  __device__ static void reset(float (&s)[S], const float (&raw)[K]) {
+    s[0] = __fadd_rn(-1.0f, __fmul_rn(2.0f, raw[0]));  // np.random.uniform(-1,1)
+    s[1] = __fadd_rn(-1.0f, __fmul_rn(2.0f, raw[1]));
+  }
+  __device__ static void obs(const float (&s)[S], float (&o)[O]) { o[0] = s[0]; o[1] = s[1]; }
+  __device__ static void step(float (&s)[S], const float (&u)[A], float& r, bool& done) {
+    s[0] = __fadd_rn(s[0], u[0]);
+    s[1] = __fadd_rn(s[1], u[1]);
+    r = -__fsqrt_rn(__fadd_rn(__fmul_rn(s[0], s[0]), __fmul_rn(s[1], s[1])));
+    done = (fabsf(s[0]) < 0.01f) && (fabsf(s[1]) < 0.01f);
+  }
+};
+
+// ---------------------------------------------------------------- rllab/envs/box2d/cartpole_env.py:13-56
+// Reduced-coordinate restatement of the Box2D model (models/cartpole.xml.mako:3-45), see oracle/envs.py.
+struct CartPoleEnvD {
+  static constexpr int KIND = B200RL_ENV_CARTPOLE, O = 4, A = 1, S = 4, K = 4, NOISE = B200RL_NOISE_UNIFORM;
+  __host__ __device__ static constexpr float lb(int) { return -10.0f; }
+  __host__ __device__ static constexpr float ub(int) { return 10.0f; }
+  __device__ static void reset(float (&s)[S], const float (&raw)[K]) {
+    const float b[4] = {2.4f * 0.05f, 4.0f * 0.05f, 0.2f * 0.05f, 4.0f * 0.05f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] = -b[i] + (2.0f * b[i]) * raw[i];
+  }
+  __device__ static void obs(const float (&s)[S], float (&o)[O]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = s[i];
+  }
+  __device__ static void step(float (&s)[S], const float (&u)[A], float& r, bool& done) {
+    const float M = 1.0f, m = 0.1f, l = 0.5f, g = 10.0f, h = 0.05f;
+    const float I = 0.1f * (0.1f * 0.1f + 1.0f) / 12.0f;
+    float x = s[0], xd = s[1], th = s[2], thd = s[3];
+    float F = fminf(fmaxf(u[0], -10.0f), 10.0f);
+    float sn, cs;
+    sincosf(th, &sn, &cs);
+    float a11 = M + m, a12 = -m * l * cs, a22 = I + m * l * l;
+    float b1 = F - m * l * sn * thd * thd;
+    float b2 = m * g * l * sn;
+    float det = a11 * a22 - a12 * a12;
+    float xdd = (a22 * b1 - a12 * b2) / det;
+    float thdd = (a11 * b2 - a12 * b1) / det;
+    xd += h * xdd;
+    thd += h * thdd;
+    x += h * xd;
+    th += h * thd;
+    s[0] = x; s[1] = xd; s[2] = th; s[3] = thd;
+    done = (fabsf(x) > 2.4f) || (fabsf(th) > 0.2f);
+    float notdone = done ? 0.0f : 1.0f;
+    float ucost = 1e-5f * (u[0] * u[0]);
+    float xcost = 1.0f - cosf(th);
+    r = notdone * 10.0f - notdone * xcost - notdone * ucost;
+  }
+};
+
+// ---------------------------------------------------------------- gym 0.7.4 Pendulum-v0 via rllab/envs/gym_env.py:58-116
+struct PendulumEnvD {
+  static constexpr int KIND = B200RL_ENV_PENDULUM, O = 3, A = 1, S = 2, K = 2, NOISE = B200RL_NOISE_UNIFORM;
+  __host__ __device__ static constexpr float lb(int) { return -2.0f; }
+  __host__ __device__ static constexpr float ub(int) { return 2.0f; }
+  __device__ static void reset(float (&s)[S], const float (&raw)[K]) {
+    const float PI = 3.14159265358979323846f;
+    s[0] = -PI + (2.0f * PI) * raw[0];
+    s[1] = -1.0f + 2.0f * raw[1];
+  }
+  __device__ static void obs(const float (&s)[S], float (&o)[O]) {
+    float sn, cs;
+    sincosf(s[0], &sn, &cs);
+    o[0] = cs; o[1] = sn; o[2] = s[1];
+  }
+  __device__ static void step(float (&s)[S], const float (&u)[A], float& r, bool& done) {
+    const float PI = 3.14159265358979323846f;
+    float th = s[0], thd = s[1];
+    float uu = fminf(fmaxf(u[0], -2.0f), 2.0f);
+    float t = th + PI;
+    float an = t - floorf(t / (2.0f * PI)) * (2.0f * PI) - PI;  // ((th+pi) mod 2pi) - pi, python-style mod
+    float cost = an * an + 0.1f * thd * thd + 0.001f * (uu * uu);
+    float nthd = thd + (-15.0f * sinf(th + PI) + 3.0f * uu) * 0.05f;
+    float nth = th + nthd * 0.05f;
+    nthd = fminf(fmaxf(nthd, -8.0f), 8.0f);
+    s[0] = nth; s[1] = nthd;
+    r = -cost;
+    done = false;
+  }
+};
+
+}  // namespace b200rl
+
+#include "planar.cuh"
+
+namespace b200rl {
+
+#ifdef B200RL_HAVE_PLANAR
+#define B200RL_PLANAR_CASES(...)                                                              \
+    case B200RL_ENV_SWIMMER: { using Env = ::b200rl::SwimmerEnvD; __VA_ARGS__; } break;       \
+    case B200RL_ENV_HOPPER: { using Env = ::b200rl::HopperEnvD; __VA_ARGS__; } break;
+#else
+#define B200RL_PLANAR_CASES(...)
+#endif
+
+// Dispatch an env kind to its struct: F is a generic lambda / functor called as f(Env{}).
+#define B200RL_DISPATCH_ENV(kind, ...)                                                        \
+  switch (kind) {                                                                             \
+    case B200RL_ENV_POINT: { using Env = ::b200rl::PointEnvD; __VA_ARGS__; } break;           \
+    case B200RL_ENV_CARTPOLE: { using Env = ::b200rl::CartPoleEnvD; __VA_ARGS__; } break;     \
+    case B200RL_ENV_PENDULUM: { using Env = ::b200rl::PendulumEnvD; __VA_ARGS__; } break;     \
+    B200RL_PLANAR_CASES(__VA_ARGS__)                                                          \
+    default:                                                                                  \
+      ::b200rl::set_error("unknown env kind %d", (int)(kind));                                \
+      return B200RL_EUNSUPPORTED;                                                             \
+  }
+
+}  // namespace b200rl

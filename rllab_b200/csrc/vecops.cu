@@ -1,0 +1,163 @@
+// P-vector kernels (float64): conjugate gradient state updates, TRPO step size, line-search parameter update,
+// Adam.  P <= a few thousand, so each op is ONE block with warp-shuffle + shared-memory reductions; everything
+// stays on the device so that a whole CG solve needs no host synchronisation.
+//
+// Replaces: rllab/misc/krylov.py:7-39 (cg), rllab/optimizers/conjugate_gradient_optimizer.py:258-275
+// (initial step size, backtracking candidates), lasagne.updates.adam as used by
+// rllab/optimizers/first_order_optimizer.py:21-22,62-65, rllab/core/parameterized.py:60-70 (set_param_values cast).
+#include "common.cuh"
+
+namespace b200rl {
+
+constexpr int VEC_THREADS = 512;
+
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < nwarp; ++w) s += scratch[w];  // fixed order, every thread computes the same value
+  return s;
+}
+
+__global__ void __launch_bounds__(VEC_THREADS)
+    cg_init_kernel(long long P, const double* __restrict__ g, double* __restrict__ x, double* __restrict__ r,
+                   double* __restrict__ p, double* __restrict__ st) {
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < P; i += blockDim.x) {
+    const double gi = g[i];
+    x[i] = 0.0; r[i] = gi; p[i] = gi;
+    acc += gi * gi;
+  }
+  const double rdotr = block_sum(acc, scratch);
+  if (threadIdx.x == 0) { st[0] = rdotr; st[1] = 0.0; st[2] = 0.0; st[3] = 0.0; }
+}
+
+// one krylov.cg iteration given z = A p  (krylov.py:25-35); a no-op once rdotr < tol was seen (the reference breaks)
+__global__ void __launch_bounds__(VEC_THREADS)
+    cg_step_kernel(long long P, const double* __restrict__ z, double* __restrict__ x, double* __restrict__ r,
+                   double* __restrict__ p, double* __restrict__ st, double tol) {
+  __shared__ double scratch[32];
+  if (st[1] != 0.0) return;  // uniform across the block
+  const double rdotr = st[0];
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < P; i += blockDim.x) acc += p[i] * z[i];
+  const double pz = block_sum(acc, scratch);
+  const double v = rdotr / pz;
+  acc = 0.0;
+  for (long long i = threadIdx.x; i < P; i += blockDim.x) {
+    x[i] += v * p[i];
+    const double ri = r[i] - v * z[i];
+    r[i] = ri;
+    acc += ri * ri;
+  }
+  const double newrdotr = block_sum(acc, scratch);
+  const double mu = newrdotr / rdotr;
+  for (long long i = threadIdx.x; i < P; i += blockDim.x) p[i] = r[i] + mu * p[i];
+  if (threadIdx.x == 0) {
+    st[0] = newrdotr;
+    st[2] = pz;
+    st[3] += 1.0;
+    if (newrdotr < tol) st[1] = 1.0;
+  }
+}
+
+__global__ void __launch_bounds__(VEC_THREADS)
+    trpo_step_size_kernel(long long P, const double* __restrict__ x, const double* __restrict__ Hx, double delta,
+                          double* __restrict__ step, double* __restrict__ info) {
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < P; i += blockDim.x) acc += x[i] * Hx[i];
+  const double xHx = block_sum(acc, scratch);
+  double beta = sqrt(2.0 * delta * (1.0 / (xHx + 1e-8)));  // conjugate_gradient_optimizer.py:260-263
+  if (isnan(beta)) beta = 1.0;                              // :264-265
+  for (long long i = threadIdx.x; i < P; i += blockDim.x) step[i] = beta * x[i];
+  if (threadIdx.x == 0) { info[0] = beta; info[1] = xHx; }
+}
+
+__global__ void axpy_params_kernel(long long P, const double* __restrict__ prev, const double* __restrict__ step,
+                                   double ratio, double* __restrict__ out, float* __restrict__ out32) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const double v = prev[i] - ratio * step[i];
+  out[i] = v;
+  out32[i] = (float)v;
+}
+
+__global__ void adam_kernel(long long P, double* __restrict__ th, float* __restrict__ th32, const double* __restrict__ g,
+                            double* __restrict__ m, double* __restrict__ v, double a_t, double b1, double b2, double eps) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const double gi = g[i];
+  const double mi = b1 * m[i] + (1.0 - b1) * gi;
+  const double vi = b2 * v[i] + (1.0 - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const double t = th[i] - a_t * mi / (sqrt(vi) + eps);
+  th[i] = t;
+  th32[i] = (float)t;
+}
+
+__global__ void f64_to_f32_kernel(long long n, const double* __restrict__ s, float* __restrict__ d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = (float)s[i];
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+extern "C" {
+
+int b200rl_cg_init(long long P, const double* g, double* x, double* r, double* p, double* cg_state, void* stream) {
+  B200RL_REQUIRE(P > 0 && g && x && r && p && cg_state, "cg_init: bad arguments");
+  cg_init_kernel<<<1, VEC_THREADS, 0, (cudaStream_t)stream>>>(P, g, x, r, p, cg_state);
+  B200RL_LAUNCH_CHECK("cg_init_kernel");
+  return 0;
+}
+
+int b200rl_cg_step(long long P, const double* z, double* x, double* r, double* p, double* cg_state,
+                   double residual_tol, void* stream) {
+  B200RL_REQUIRE(P > 0 && z && x && r && p && cg_state, "cg_step: bad arguments");
+  cg_step_kernel<<<1, VEC_THREADS, 0, (cudaStream_t)stream>>>(P, z, x, r, p, cg_state, residual_tol);
+  B200RL_LAUNCH_CHECK("cg_step_kernel");
+  return 0;
+}
+
+int b200rl_trpo_step_size(long long P, const double* x, const double* Hx, double max_constraint_val,
+                          double* step_out, double* info_out, void* stream) {
+  B200RL_REQUIRE(P > 0 && x && Hx && step_out && info_out, "trpo_step_size: bad arguments");
+  trpo_step_size_kernel<<<1, VEC_THREADS, 0, (cudaStream_t)stream>>>(P, x, Hx, max_constraint_val, step_out,
+                                                                      info_out);
+  B200RL_LAUNCH_CHECK("trpo_step_size_kernel");
+  return 0;
+}
+
+int b200rl_axpy_params(long long P, const double* theta_prev, const double* step, double ratio, double* theta_out,
+                       float* theta_f32_out, void* stream) {
+  B200RL_REQUIRE(P > 0 && theta_prev && step && theta_out && theta_f32_out, "axpy_params: bad arguments");
+  axpy_params_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, theta_prev, step, ratio,
+                                                                                     theta_out, theta_f32_out);
+  B200RL_LAUNCH_CHECK("axpy_params_kernel");
+  return 0;
+}
+
+int b200rl_adam_step(long long P, double* theta, float* theta_f32, const double* g, double* m, double* v, long long t,
+                     double lr, double b1, double b2, double eps, void* stream) {
+  B200RL_REQUIRE(P > 0 && theta && theta_f32 && g && m && v && t >= 1, "adam_step: bad arguments");
+  const double a_t = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
+  adam_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, theta, theta_f32, g, m, v, a_t, b1,
+                                                                              b2, eps);
+  B200RL_LAUNCH_CHECK("adam_kernel");
+  return 0;
+}
+
+int b200rl_f64_to_f32(long long n, const double* src, float* dst, void* stream) {
+  B200RL_REQUIRE(n > 0 && src && dst, "f64_to_f32: bad arguments");
+  f64_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, src, dst);
+  B200RL_LAUNCH_CHECK("f64_to_f32_kernel");
+  return 0;
+}
+}

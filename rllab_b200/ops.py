@@ -1,0 +1,185 @@
+"""Device operations of the hot path as thin, typed wrappers over the C ABI (rllab_b200/_lib.py).
+
+Tensors are torch CUDA tensors used purely as array containers (no autograd anywhere); every wrapper validates
+dtype/shape/contiguity, passes raw pointers + the current CUDA stream, and raises on failure.
+Layouts are documented in include/b200rl.h.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+F32, F64, U8, U16 = torch.float32, torch.float64, torch.uint8, torch.uint16
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype, name, numel=None):
+    if t is None:
+        return
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise ValueError("%s must be a contiguous CUDA tensor of dtype %s (got %s, cuda=%s)" %
+                         (name, dtype, t.dtype, t.is_cuda))
+    if numel is not None and t.numel() != numel:
+        raise ValueError("%s must have %d elements, has %d" % (name, numel, t.numel()))
+
+
+_ws_cache = {}
+
+
+def workspace(device):
+    """float64 reduction workspace (b200rl_ws_doubles entries), one per device, allocated once."""
+    key = torch.device(device).index
+    ws = _ws_cache.get(key)
+    if ws is None:
+        n = int(L.load().b200rl_ws_doubles())
+        ws = torch.empty(n, dtype=F64, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+class LaneBatch(object):
+    """Device trajectory buffers of one rollout: N lanes x T steps (layout of include/b200rl.h)."""
+
+    def __init__(self, O, A, N, T, device):
+        self.O, self.A, self.N, self.T = O, A, N, T
+        self.device = device
+        self.obs = torch.empty((O, T, N), dtype=F32, device=device)
+        self.act = torch.empty((A, T, N), dtype=F32, device=device)
+        self.mean = torch.empty((A, T, N), dtype=F32, device=device)
+        self.rew = torch.empty((T, N), dtype=F32, device=device)
+        self.flags = torch.empty((T, N), dtype=U8, device=device)
+        self.tstep = torch.empty((T, N), dtype=U16, device=device)
+        self.log_std = torch.empty((A,), dtype=F32, device=device)
+        self.adv = torch.empty((T, N), dtype=F32, device=device)
+        self.ret = torch.empty((T, N), dtype=F32, device=device)
+        self.base = torch.empty((T, N), dtype=F32, device=device)
+        self.sums = torch.zeros((L.PS_NSUM,), dtype=F64, device=device)
+        self.maxs = torch.zeros((L.PS_NMAX,), dtype=F64, device=device)
+
+    @property
+    def B(self):
+        return self.N * self.T
+
+    def to_numpy(self):
+        """Host copy in the oracle's dict layout (tests / path materialisation)."""
+        return dict(obs=self.obs.cpu().numpy(), act=self.act.cpu().numpy(), mean=self.mean.cpu().numpy(),
+                    rew=self.rew.cpu().numpy(), flags=self.flags.cpu().numpy(),
+                    tstep=self.tstep.cpu().view(torch.int16).numpy().view(np.uint16),
+                    log_std=self.log_std.cpu().numpy())
+
+
+def fill_noise(out, rows, row0, K, N, lane0, kind, seed, it, stream_id):
+    _chk(out, F32, "out", rows * K * N)
+    L.call("b200rl_fill_noise", L.ptr(out), rows, row0, K, N, lane0, kind, seed, it, stream_id, _stream())
+
+
+def env_reset(kind, N, state, obs_out, reset_raw=None, seed=0, it=0, row=0, lane0=0):
+    _chk(state, F32, "state"), _chk(obs_out, F32, "obs_out"), _chk(reset_raw, F32, "reset_raw")
+    L.call("b200rl_env_reset", kind, N, L.ptr(state), L.ptr(obs_out), L.ptr(reset_raw), seed, it, row, lane0, _stream())
+
+
+def env_step(kind, N, state, actions, obs_out, rew_out, done_out):
+    _chk(state, F32, "state"), _chk(actions, F32, "actions"), _chk(obs_out, F32, "obs_out")
+    _chk(rew_out, F32, "rew_out", N), _chk(done_out, U8, "done_out", N)
+    L.call("b200rl_env_step", kind, N, L.ptr(state), L.ptr(actions), L.ptr(obs_out), L.ptr(rew_out), L.ptr(done_out),
+           _stream())
+
+
+def policy_get_actions(params32, O, h1, h2, A, min_std, obs, n, eps, seed, it, row, lane0, act_out, mean_out, log_std_out):
+    _chk(params32, F32, "params32"), _chk(obs, F32, "obs", O * n), _chk(eps, F32, "eps")
+    _chk(act_out, F32, "act_out", A * n), _chk(mean_out, F32, "mean_out", A * n), _chk(log_std_out, F32, "log_std_out", A)
+    L.call("b200rl_policy_get_actions", L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), L.ptr(obs), n, L.ptr(eps),
+           seed, it, row, lane0, L.ptr(act_out), L.ptr(mean_out), L.ptr(log_std_out), _stream())
+
+
+def rollout(kind, params32, h1, h2, min_std, batch, max_path_length, eps=None, reset_raw=None, seed=0, it=0, lane0=0):
+    b = batch
+    _chk(params32, F32, "params32"), _chk(eps, F32, "eps"), _chk(reset_raw, F32, "reset_raw")
+    L.call("b200rl_rollout", kind, L.ptr(params32), h1, h2, float(min_std or 0.0), b.N, b.T, max_path_length,
+           L.ptr(eps), L.ptr(reset_raw), seed, it, lane0, L.ptr(b.obs), L.ptr(b.act), L.ptr(b.mean), L.ptr(b.rew),
+           L.ptr(b.flags), L.ptr(b.tstep), L.ptr(b.log_std), _stream())
+
+
+def process_samples(batch, w, discount, gae_lambda):
+    b = batch
+    _chk(w, F64, "w", 2 * b.O + 4)
+    L.call("b200rl_process_samples", b.O, b.N, b.T, L.ptr(b.obs), L.ptr(b.rew), L.ptr(b.flags), L.ptr(b.tstep),
+           L.ptr(w), float(discount), float(gae_lambda), L.ptr(b.adv), L.ptr(b.ret), L.ptr(b.base), L.ptr(b.sums),
+           L.ptr(b.maxs), L.ptr(workspace(b.device)), _stream())
+
+
+def center_advantages(batch, center, positive):
+    b = batch
+    L.call("b200rl_center_advantages", L.ptr(b.adv), b.B, L.ptr(b.sums), L.ptr(b.maxs), int(center), int(positive),
+           _stream())
+
+
+def lfb_gram(batch, gram_out):
+    b = batch
+    d1 = 2 * b.O + 5
+    _chk(gram_out, F64, "gram_out", d1 * (d1 + 1) // 2)
+    L.call("b200rl_lfb_gram", b.O, b.B, L.ptr(b.obs), L.ptr(b.tstep), L.ptr(b.ret), L.ptr(gram_out),
+           L.ptr(workspace(b.device)), _stream())
+
+
+def loss_kl(loss_kind, params32, dims, min_std, batch, scale, out):
+    O, h1, h2, A = dims
+    b = batch
+    _chk(params32, F32, "params32"), _chk(out, F64, "out", 3)
+    L.call("b200rl_loss_kl", loss_kind, L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
+           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), float(scale), L.ptr(out),
+           L.ptr(workspace(b.device)), _stream())
+
+
+def grad(loss_kind, params32, dims, min_std, batch, scale, g_out):
+    O, h1, h2, A = dims
+    b = batch
+    _chk(params32, F32, "params32"), _chk(g_out, F64, "g_out")
+    L.call("b200rl_grad", loss_kind, L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
+           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), float(scale), L.ptr(g_out),
+           L.ptr(workspace(b.device)), _stream())
+
+
+def fvp(params32, dims, min_std, batch, x, scale, reg_coeff, diag_scale, Hx_out):
+    O, h1, h2, A = dims
+    b = batch
+    _chk(params32, F32, "params32"), _chk(x, F64, "x"), _chk(Hx_out, F64, "Hx_out", x.numel())
+    L.call("b200rl_fvp", L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs), L.ptr(x),
+           float(scale), float(reg_coeff), float(diag_scale), L.ptr(Hx_out), L.ptr(workspace(b.device)), _stream())
+
+
+def cg_init(g, x, r, p, st):
+    L.call("b200rl_cg_init", g.numel(), L.ptr(g), L.ptr(x), L.ptr(r), L.ptr(p), L.ptr(st), _stream())
+
+
+def cg_step(z, x, r, p, st, tol=1e-10):
+    L.call("b200rl_cg_step", z.numel(), L.ptr(z), L.ptr(x), L.ptr(r), L.ptr(p), L.ptr(st), float(tol), _stream())
+
+
+def trpo_step_size(x, Hx, delta, step_out, info_out):
+    L.call("b200rl_trpo_step_size", x.numel(), L.ptr(x), L.ptr(Hx), float(delta), L.ptr(step_out), L.ptr(info_out),
+           _stream())
+
+
+def axpy_params(prev, step, ratio, out64, out32):
+    L.call("b200rl_axpy_params", prev.numel(), L.ptr(prev), L.ptr(step), float(ratio), L.ptr(out64), L.ptr(out32),
+           _stream())
+
+
+def adam_step(theta64, theta32, g, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    L.call("b200rl_adam_step", theta64.numel(), L.ptr(theta64), L.ptr(theta32), L.ptr(g), L.ptr(m), L.ptr(v), int(t),
+           float(lr), float(b1), float(b2), float(eps), _stream())
+
+
+def f64_to_f32(src, dst):
+    L.call("b200rl_f64_to_f32", src.numel(), L.ptr(src), L.ptr(dst), _stream())
+
+
+def planes_to_rows_f64(src, dim, B, dst):
+    _chk(src, F32, "src", dim * B), _chk(dst, F64, "dst", dim * B)
+    L.call("b200rl_planes_to_rows_f64", dim, B, L.ptr(src), L.ptr(dst), _stream())

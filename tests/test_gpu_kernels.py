@@ -1,0 +1,419 @@
+"""GPU parity tests: every CUDA kernel of libb200rl.so against the CPU oracle (oracle/*.py) on identical inputs.
+Integer / index work (flags, tstep, path counts) and PointEnv arithmetic: bit-exact.  Floating point: tolerances
+stated per test (float32 kernels vs float64 oracle)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import envs as E            # noqa: E402
+from oracle import optim as OPT         # noqa: E402
+from oracle import philox as PH         # noqa: E402
+from oracle import policy as P          # noqa: E402
+from oracle import sampler as S         # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rllab_b200 import _lib
+    _lib.load()                          # fails loudly if the extension is missing
+    return torch.device("cuda:0")
+
+
+def _ops():
+    from rllab_b200 import ops
+    return ops
+
+
+def _L():
+    from rllab_b200 import _lib
+    return _lib
+
+
+ENVS = ["point", "cartpole", "pendulum"]
+try:
+    from oracle import planar as _planar      # noqa: F401
+    ENVS += ["swimmer", "hopper"]
+except Exception:                             # pragma: no cover
+    pass
+
+
+def _mk(env_name, hidden, seed=0):
+    env64 = E.make(env_name)
+    dims = P.Dims(env64.O, (hidden, hidden), env64.A)
+    theta = P.init_params(dims, np.random.RandomState(seed))
+    theta += np.random.RandomState(seed + 1).randn(dims.P) * 0.05     # non-zero biases
+    theta[-env64.A:] = -0.5 + 0.1 * np.arange(env64.A)               # log_std
+    return env64, dims, theta
+
+
+def _noise(ops, L, env, N, T, dev, seed=3, it=5):
+    eps = torch.empty((T, env.A, N), dtype=torch.float32, device=dev)
+    ops.fill_noise(eps, T, 0, env.A, N, 0, L.NOISE_NORMAL, seed, it, 0)
+    kind = L.NOISE_UNIFORM if env.noise_kind == "uniform" else L.NOISE_NORMAL
+    rr = torch.empty((T + 1, env.K, N), dtype=torch.float32, device=dev)
+    ops.fill_noise(rr, T + 1, 0, env.K, N, 0, kind, seed, it, 1)
+    return eps, rr
+
+
+def _gpu_rollout(env_name, hidden, N, T, mpl, dev, inject=True, seed=3, it=5):
+    ops, L = _ops(), _L()
+    env, dims, theta = _mk(env_name, hidden)
+    th32 = torch.tensor(theta, dtype=torch.float32, device=dev)
+    b = ops.LaneBatch(env.O, env.A, N, T, dev)
+    eps, rr = _noise(ops, L, env, N, T, dev, seed, it)
+    if inject:
+        ops.rollout(L.ENV_KINDS[env_name], th32, hidden, hidden, 1e-6, b, mpl, eps, rr, seed, it)
+    else:
+        ops.rollout(L.ENV_KINDS[env_name], th32, hidden, hidden, 1e-6, b, mpl, None, None, seed, it)
+    torch.cuda.synchronize()
+    return env, dims, th32.cpu().numpy().astype(np.float64), b, eps.cpu().numpy(), rr.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------- noise
+def test_philox_stream_matches_oracle(dev):
+    ops, L = _ops(), _L()
+    rows, K, N = 5, 4, 257
+    out = torch.empty((rows, K, N), dtype=torch.float32, device=dev)
+    ops.fill_noise(out, rows, 2, K, N, 1000, L.NOISE_UNIFORM, 11, 7, 1)
+    raw = PH.raw_block(rows, 2, K, N, 1000, 11, 7, 1)
+    assert np.array_equal(out.cpu().numpy(), PH.uniform_from_raw(raw))       # integer stream: bit-exact
+    ops.fill_noise(out, rows, 2, K, N, 1000, L.NOISE_NORMAL, 11, 7, 0)
+    raw = PH.raw_block(rows, 2, K, N, 1000, 11, 7, 0)
+    np.testing.assert_allclose(out.cpu().numpy(), PH.normal_from_raw(raw), rtol=2e-5, atol=2e-6)
+    big = torch.empty((64, 2, 4096), dtype=torch.float32, device=dev)
+    ops.fill_noise(big, 64, 0, 2, 4096, 0, L.NOISE_NORMAL, 1, 0, 0)
+    x = big.cpu().numpy().astype(np.float64)
+    assert abs(x.mean()) < 5e-3 and abs(x.std() - 1.0) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------- env step
+@pytest.mark.parametrize("env_name", ENVS)
+def test_env_step_matches_oracle(dev, env_name):
+    ops, L = _ops(), _L()
+    env32 = E.make(env_name, np.float32)
+    kind = L.ENV_KINDS[env_name]
+    info = L.env_info(kind)
+    assert (info["obs_dim"], info["act_dim"], info["state_dim"], info["reset_dim"]) == (env32.O, env32.A, env32.S, env32.K)
+    N, steps = 512, 25
+    rng = np.random.RandomState(0)
+    raw = rng.rand(env32.K, N).astype(np.float32) if env32.noise_kind == "uniform" else \
+        rng.randn(env32.K, N).astype(np.float32)
+    state = torch.empty((env32.S, N), dtype=torch.float32, device=dev)
+    obs = torch.empty((env32.O, N), dtype=torch.float32, device=dev)
+    rew = torch.empty((N,), dtype=torch.float32, device=dev)
+    done = torch.empty((N,), dtype=torch.uint8, device=dev)
+    ops.env_reset(kind, N, state, obs, torch.tensor(raw, device=dev))
+    s = env32.reset(raw)
+    exact = env_name == "point"
+    tol = dict(rtol=0, atol=0) if exact else dict(rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(obs.cpu().numpy(), env32.obs(s), **tol)
+    for t in range(steps):
+        a = (rng.randn(env32.A, N) * 0.7).astype(np.float32)
+        ops.env_step(kind, N, state, torch.tensor(a, device=dev), obs, rew, done)
+        s, r, d = env32.step(s, env32.scale_action(a))
+        if exact:
+            assert np.array_equal(obs.cpu().numpy(), env32.obs(s))          # PointEnv: bit-identical
+            assert np.array_equal(rew.cpu().numpy(), r)
+            assert np.array_equal(done.cpu().numpy().astype(bool), d)
+        else:
+            # re-sync the oracle to the device state each step so that errors do not compound chaotically
+            np.testing.assert_allclose(obs.cpu().numpy(), env32.obs(s), rtol=2e-4, atol=5e-5)
+            np.testing.assert_allclose(rew.cpu().numpy(), r, rtol=2e-4, atol=5e-4)
+            dd = done.cpu().numpy().astype(bool)
+            assert (dd != d).mean() < 0.01
+            s = state.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------- fused rollout
+@pytest.mark.parametrize("env_name,hidden", [(e, 32) for e in ENVS] + [("cartpole", 64)])
+def test_rollout_matches_oracle(dev, env_name, hidden):
+    N, T, mpl = 256, 40, 17
+    env, dims, theta, b, eps, rr = _gpu_rollout(env_name, hidden, N, T, mpl, dev)
+    env32 = E.make(env_name, np.float32)
+    traj = b.to_numpy()
+    ref = S.rollout_lanes(env32, theta, dims, N, T, mpl, eps, rr)
+    # integer/index work: identical except where a done threshold is within float noise
+    mism = (traj["flags"] != ref["flags"]).any(axis=0)
+    assert mism.mean() < 0.02
+    ok = ~mism
+    assert np.array_equal(traj["tstep"][:, ok], ref["tstep"][:, ok])
+    for k, tol in (("obs", 2e-3), ("act", 2e-3), ("mean", 2e-3), ("rew", 5e-3)):
+        np.testing.assert_allclose(traj[k][..., ok], ref[k][..., ok], rtol=tol, atol=tol, err_msg=k)
+    np.testing.assert_allclose(traj["log_std"], ref["log_std"], rtol=1e-6)
+    # one-step policy parity at float32 resolution: mean(obs) against the float64 oracle on the DEVICE's obs
+    mu, _ = P.forward(theta, traj["obs"].reshape(env.O, -1).T, dims)
+    np.testing.assert_allclose(traj["mean"].reshape(env.A, -1).T, mu, rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("env_name", ENVS)
+def test_rollout_replay_index_work_exact(dev, env_name):
+    """Replay the device's own recorded actions through the float32 oracle env: PointEnv obs/rew/flags/tstep must be
+    bit-identical; the other envs agree to float32 tolerance with identical flags away from thresholds."""
+    N, T, mpl = 128, 60, 23
+    env, dims, theta, b, eps, rr = _gpu_rollout(env_name, 32, N, T, mpl, dev)
+    env32 = E.make(env_name, np.float32)
+    traj = b.to_numpy()
+    s = env32.reset(rr[0])
+    plen = np.zeros(N, np.int64)
+    for t in range(T):
+        o = env32.obs(s)
+        s2, r, d = env32.step(s, env32.scale_action(traj["act"][:, t]))
+        plen1 = plen + 1
+        end = d | (plen1 >= mpl) | (t == T - 1)
+        fl = d.astype(np.uint8) * 1 + end.astype(np.uint8) * 2
+        if env_name == "point":
+            assert np.array_equal(traj["obs"][:, t], o)
+            assert np.array_equal(traj["rew"][t], r)
+            assert np.array_equal(traj["flags"][t], fl)
+            assert np.array_equal(traj["tstep"][t], plen.astype(np.uint16))
+        else:
+            np.testing.assert_allclose(traj["obs"][:, t], o, rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(traj["rew"][t], r, rtol=1e-4, atol=2e-4)
+            assert (traj["flags"][t] != fl).mean() < 0.02
+        # follow the device's bookkeeping so one threshold flip does not cascade
+        end_dev = (traj["flags"][t] & 2) != 0
+        fresh = env32.reset(rr[t + 1])
+        s = np.where(end_dev[None], fresh, s2).astype(np.float32)
+        plen = np.where(end_dev, 0, plen1)
+    paths = S.lanes_to_paths(traj)
+    assert sum(len(p["rewards"]) for p in paths) == N * T                      # every sample belongs to one path
+    assert max(len(p["rewards"]) for p in paths) <= mpl
+
+
+@pytest.mark.parametrize("env_name", ["point", "cartpole"])
+def test_rollout_internal_philox_equals_injected(dev, env_name):
+    N, T, mpl = 200, 30, 11
+    _, _, _, b1, _, _ = _gpu_rollout(env_name, 32, N, T, mpl, dev, inject=True)
+    _, _, _, b2, _, _ = _gpu_rollout(env_name, 32, N, T, mpl, dev, inject=False)
+    for k in ("obs", "act", "mean", "rew", "flags"):
+        assert torch.equal(getattr(b1, k), getattr(b2, k)), k
+    assert torch.equal(b1.tstep.view(torch.int16), b2.tstep.view(torch.int16))
+
+
+def test_policy_get_actions_matches_rollout_forward(dev):
+    ops, L = _ops(), _L()
+    env, dims, theta = _mk("cartpole", 32)
+    th32 = torch.tensor(theta, dtype=torch.float32, device=dev)
+    n = 777
+    obs = torch.randn((4, n), device=dev)
+    eps = torch.randn((1, n), device=dev)
+    act = torch.empty((1, n), device=dev)
+    mean = torch.empty((1, n), device=dev)
+    ls = torch.empty((1,), device=dev)
+    ops.policy_get_actions(th32, 4, 32, 32, 1, 1e-6, obs, n, eps, 0, 0, 0, 0, act, mean, ls)
+    mu, lsd = P.forward(th32.cpu().numpy().astype(np.float64), obs.cpu().numpy().T.astype(np.float64), dims)
+    np.testing.assert_allclose(mean.cpu().numpy().T, mu, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(act.cpu().numpy().T, mu + np.exp(lsd) * eps.cpu().numpy().T, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(ls.cpu().numpy(), lsd, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------- process_samples
+def _batch_from_numpy(ops, traj, dev):
+    O, T, N = traj["obs"].shape
+    A = traj["act"].shape[0]
+    b = ops.LaneBatch(O, A, N, T, dev)
+    b.obs.copy_(torch.tensor(traj["obs"], dtype=torch.float32))
+    b.act.copy_(torch.tensor(traj["act"], dtype=torch.float32))
+    b.mean.copy_(torch.tensor(traj["mean"], dtype=torch.float32))
+    b.rew.copy_(torch.tensor(traj["rew"], dtype=torch.float32))
+    b.flags.copy_(torch.tensor(traj["flags"]))
+    b.tstep.copy_(torch.tensor(traj["tstep"].view(np.int16)).view(torch.uint16))
+    b.log_std.copy_(torch.tensor(traj["log_std"], dtype=torch.float32))
+    return b
+
+
+def _stats_from_device(b):
+    s = b.sums.cpu().numpy()
+    m = b.maxs.cpu().numpy()
+    n_paths = s[3]
+    avg_ret = s[5] / n_paths
+    vary = s[8] / s[2] - (s[7] / s[2]) ** 2
+    varres = s[12] / s[2] - (s[11] / s[2]) ** 2
+    return dict(AverageDiscountedReturn=s[4] / n_paths, AverageReturn=avg_ret, NumTrajs=int(round(n_paths)),
+                StdReturn=np.sqrt(max(s[6] / n_paths - avg_ret ** 2, 0.0)), MaxReturn=m[0], MinReturn=-m[1],
+                ExplainedVariance=1 - varres / (vary + 1e-8),
+                adv_mean=s[0] / s[2], adv_std=np.sqrt(max(s[1] / s[2] - (s[0] / s[2]) ** 2, 0.0)))
+
+
+def test_process_samples_matches_reference_golden(dev, golden):
+    """The committed golden vectors were produced by the reference's own BaseSampler.process_samples."""
+    ops = _ops()
+    g = golden
+    traj = {k[len("ps_in_"):]: v for k, v in g.items() if k.startswith("ps_in_") and k != "ps_in_coeffs_prev"}
+    # the kernels hold float32 trajectories: feed the reference numbers rounded to float32 and compare at that level
+    for tag, coeffs in (("a", None), ("b", g["ps_in_coeffs_prev"]), ("c", g["ps_in_coeffs_prev"])):
+        disc, lam, center, positive = g["ps_%s_cfg" % tag]
+        b = _batch_from_numpy(ops, traj, dev)
+        w = None if coeffs is None else torch.tensor(coeffs, dtype=torch.float64, device=dev)
+        ops.process_samples(b, w, disc, lam)
+        np.testing.assert_allclose(b.ret.cpu().numpy(), g["ps_%s_ret" % tag], rtol=2e-6, atol=2e-6)
+        st = _stats_from_device(b)
+        assert st["NumTrajs"] == int(g["ps_%s_NumTrajs" % tag])                      # integer: exact
+        for key in ("AverageDiscountedReturn", "AverageReturn", "StdReturn", "MaxReturn", "MinReturn",
+                    "ExplainedVariance"):
+            np.testing.assert_allclose(st[key], g["ps_%s_%s" % (tag, key)], rtol=5e-5, atol=5e-6, err_msg=key)
+        ops.center_advantages(b, bool(center), bool(positive))
+        np.testing.assert_allclose(b.adv.cpu().numpy(), g["ps_%s_adv" % tag], rtol=5e-5, atol=5e-5)
+        # baseline fit: normal equations on the device, tiny solve on the host exactly as the reference does
+        d1 = 2 * b.O + 5
+        gram = torch.empty((d1 * (d1 + 1) // 2,), dtype=torch.float64, device=dev)
+        ops.lfb_gram(b, gram)
+        G = np.zeros((d1, d1))
+        G[np.triu_indices(d1)] = gram.cpu().numpy()
+        G = G + G.T - np.diag(np.diag(G))
+        fit = S.lfb_fit_normal(G[:-1, :-1], G[:-1, -1])
+        ref_fit = g["ps_%s_fit" % tag]
+        pred_dev = S.lfb_features_lanes(traj["obs"], traj["tstep"]).reshape(d1 - 1, -1).T @ fit
+        pred_ref = S.lfb_features_lanes(traj["obs"], traj["tstep"]).reshape(d1 - 1, -1).T @ ref_fit
+        np.testing.assert_allclose(pred_dev, pred_ref, rtol=2e-3, atol=2e-3)   # ill-conditioned d=10 on 161 samples
+
+
+@pytest.mark.parametrize("env_name", ["cartpole", "pendulum"])
+def test_process_samples_matches_oracle_large(dev, env_name):
+    ops = _ops()
+    N, T, mpl = 1024, 64, 40
+    env, dims, theta, b, eps, rr = _gpu_rollout(env_name, 32, N, T, mpl, dev)
+    traj = b.to_numpy()
+    w = np.random.RandomState(5).randn(2 * env.O + 4) * 0.3
+    ops.process_samples(b, torch.tensor(w, dtype=torch.float64, device=dev), 0.99, 0.95)
+    ref = S.process_samples_lanes(traj, w, 0.99, 0.95, center_adv=True)
+    np.testing.assert_allclose(b.ret.cpu().numpy(), ref["ret"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(b.base.cpu().numpy(), ref["base"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(b.adv.cpu().numpy(), ref["adv_raw"], rtol=1e-5, atol=2e-4)
+    st = _stats_from_device(b)
+    for key in ("AverageDiscountedReturn", "AverageReturn", "StdReturn", "MaxReturn", "MinReturn", "ExplainedVariance",
+                "adv_mean", "adv_std"):
+        np.testing.assert_allclose(st[key], ref["stats"][key], rtol=1e-6, atol=1e-6, err_msg=key)
+    assert st["NumTrajs"] == ref["stats"]["NumTrajs"]
+    ops.center_advantages(b, True, False)
+    np.testing.assert_allclose(b.adv.cpu().numpy(), ref["adv"], rtol=1e-4, atol=1e-5)
+    d1 = 2 * b.O + 5
+    gram = torch.empty((d1 * (d1 + 1) // 2,), dtype=torch.float64, device=dev)
+    ops.lfb_gram(b, gram)
+    F = S.lfb_features_lanes(traj["obs"], traj["tstep"]).reshape(d1 - 1, -1)
+    F = np.concatenate([F, ref["ret"].reshape(1, -1)], axis=0)
+    G = (F @ F.T)[np.triu_indices(d1)]
+    np.testing.assert_allclose(gram.cpu().numpy(), G, rtol=2e-5, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------- update kernels
+def _update_setup(dev, env_name, hidden, N=512, T=32):
+    ops = _ops()
+    env, dims, theta, b, eps, rr = _gpu_rollout(env_name, hidden, N, T, 20, dev)
+    traj = b.to_numpy()
+    ops.process_samples(b, None, 0.99, 1.0)
+    ops.center_advantages(b, True, False)
+    torch.cuda.synchronize()
+    batch = S.batch_from_traj(traj, b.adv.cpu().numpy())
+    return ops, env, dims, theta, b, batch
+
+
+@pytest.mark.parametrize("env_name,hidden", [("cartpole", 32), ("point", 32), ("pendulum", 32), ("cartpole", 64)])
+def test_loss_kl_grad_fvp_match_oracle(dev, env_name, hidden):
+    L = _L()
+    ops, env, dims, theta, b, batch = _update_setup(dev, env_name, hidden)
+    dd = (env.O, hidden, hidden, env.A)
+    B = b.B
+    th32 = torch.tensor(theta, dtype=torch.float32, device=dev)
+    out = torch.zeros(3, dtype=torch.float64, device=dev)
+    # at theta_old: likelihood ratio == 1 exactly (same canonical summation order in rollout and update kernels)
+    ops.loss_kl(L.LOSS_TRPO, th32, dd, 1e-6, b, 1.0 / B, out)
+    o = out.cpu().numpy()
+    assert abs(o[0] + batch["adv"].mean()) < 1e-9 and abs(o[1]) < 1e-12 and abs(o[2]) < 1e-12
+    # perturbed parameters: loss / KL / gradient against the float64 oracle
+    rng = np.random.RandomState(9)
+    th2 = theta + rng.randn(dims.P) * 0.02
+    th2_32 = torch.tensor(th2, dtype=torch.float32, device=dev)
+    th2 = th2_32.cpu().numpy().astype(np.float64)
+    for kind, name in ((L.LOSS_TRPO, "trpo"), (L.LOSS_VPG, "vpg")):
+        ops.loss_kl(kind, th2_32, dd, 1e-6, b, 1.0 / B, out)
+        o = out.cpu().numpy()
+        ref_loss = P.surr_loss_trpo(th2, batch, dims) if name == "trpo" else P.surr_loss_vpg(th2, batch, dims)
+        mkl, xkl = P.kl_stats(th2, batch, dims)
+        np.testing.assert_allclose(o[0], ref_loss, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(o[1], mkl, rtol=2e-5, atol=1e-8)
+        np.testing.assert_allclose(o[2], xkl, rtol=1e-4, atol=1e-8)
+        g = torch.zeros(dims.P, dtype=torch.float64, device=dev)
+        ops.grad(kind, th2_32, dd, 1e-6, b, 1.0 / B, g)
+        ref_g = P.grad_surr(th2, batch, dims, name)
+        np.testing.assert_allclose(g.cpu().numpy(), ref_g, rtol=2e-4, atol=2e-6 * np.abs(ref_g).max() + 1e-9)
+    # Fisher-vector product at theta_old
+    x = rng.randn(dims.P)
+    xd = torch.tensor(x, dtype=torch.float64, device=dev)
+    Hx = torch.zeros(dims.P, dtype=torch.float64, device=dev)
+    ops.fvp(th32, dd, 1e-6, b, xd, 1.0 / B, 1e-5, 1.0, Hx)
+    x32 = x.astype(np.float32).astype(np.float64)          # the kernel rounds the tangent to float32
+    ref_Hx = P.fvp(theta, batch, x32, dims, 0.0) + 1e-5 * x
+    np.testing.assert_allclose(Hx.cpu().numpy(), ref_Hx, rtol=2e-4, atol=2e-6 * np.abs(ref_Hx).max())
+
+
+def test_min_std_clamp_blocks_logstd_gradient(dev):
+    L = _L()
+    ops, env, dims, theta, b, batch = _update_setup(dev, "cartpole", 32)
+    th = theta.copy()
+    th[-1] = np.log(1e-3) - 1.0            # below log(min_std=1e-3)
+    dd = (env.O, 32, 32, env.A)
+    g = torch.zeros(dims.P, dtype=torch.float64, device=dev)
+    th32 = torch.tensor(th, dtype=torch.float32, device=dev)
+    ops.grad(L.LOSS_VPG, th32, dd, 1e-3, b, 1.0 / b.B, g)
+    ref = P.grad_surr(th32.cpu().numpy().astype(np.float64), batch, dims, "vpg", min_std=1e-3)
+    assert g.cpu().numpy()[-1] == 0.0 and ref[-1] == 0.0
+    np.testing.assert_allclose(g.cpu().numpy(), ref, rtol=5e-4, atol=1e-6 * np.abs(ref).max() + 1e-9)
+
+
+# ------------------------------------------------------------------------------------------- vector kernels
+def test_cg_kernels_match_reference_golden(dev, golden):
+    ops = _ops()
+    A = torch.tensor(golden["cg_A"], dtype=torch.float64, device=dev)
+    bvec = torch.tensor(golden["cg_b"], dtype=torch.float64, device=dev)
+    for iters, key in ((10, "cg_x10"), (3, "cg_x3")):
+        x, r, p = (torch.empty_like(bvec) for _ in range(3))
+        st = torch.zeros(4, dtype=torch.float64, device=dev)
+        ops.cg_init(bvec, x, r, p, st)
+        for _ in range(iters):
+            z = (A @ p).contiguous()      # test plumbing only: the product path uses b200rl_fvp here
+            ops.cg_step(z, x, r, p, st)
+        np.testing.assert_allclose(x.cpu().numpy(), golden[key], rtol=1e-9, atol=1e-12)
+    # early exit emulation: once rdotr < tol the state freezes (krylov.py:36-37 break)
+    x, r, p = (torch.empty_like(bvec) for _ in range(3))
+    st = torch.zeros(4, dtype=torch.float64, device=dev)
+    ops.cg_init(bvec, x, r, p, st)
+    for _ in range(40):
+        ops.cg_step((A @ p).contiguous(), x, r, p, st, 1e-10)
+    ref = OPT.cg(lambda v: golden["cg_A"] @ v, golden["cg_b"].copy(), 40)
+    np.testing.assert_allclose(x.cpu().numpy(), ref, rtol=1e-7, atol=1e-10)
+    assert st.cpu().numpy()[1] == 1.0 and st.cpu().numpy()[3] < 40
+
+
+def test_step_size_axpy_adam_match_oracle(dev):
+    ops = _ops()
+    rng = np.random.RandomState(2)
+    Pn = 1250
+    x, Hx, th = rng.randn(Pn), rng.randn(Pn), rng.randn(Pn)
+    Hx = np.abs(Hx) * np.sign(x)          # x.Hx > 0
+    xd, Hd, td = (torch.tensor(v, dtype=torch.float64, device=dev) for v in (x, Hx, th))
+    step = torch.empty_like(xd)
+    info = torch.zeros(2, dtype=torch.float64, device=dev)
+    ops.trpo_step_size(xd, Hd, 0.01, step, info)
+    beta = np.sqrt(2.0 * 0.01 * (1.0 / (x.dot(Hx) + 1e-8)))
+    np.testing.assert_allclose(info.cpu().numpy()[0], beta, rtol=1e-12)
+    np.testing.assert_allclose(step.cpu().numpy(), beta * x, rtol=1e-12)
+    ops.trpo_step_size(xd, -Hd, 0.01, step, info)            # negative curvature -> NaN -> 1 (cg_opt.py:264-265)
+    assert info.cpu().numpy()[0] == 1.0
+    out64 = torch.empty_like(td)
+    out32 = torch.empty(Pn, dtype=torch.float32, device=dev)
+    ops.axpy_params(td, step, 0.8 ** 3, out64, out32)
+    np.testing.assert_allclose(out64.cpu().numpy(), th - 0.8 ** 3 * step.cpu().numpy(), rtol=1e-14)
+    assert np.array_equal(out32.cpu().numpy(), out64.cpu().numpy().astype(np.float32))
+    m = torch.zeros_like(td)
+    v = torch.zeros_like(td)
+    th_o, m_o, v_o, t_o = th.copy(), np.zeros(Pn), np.zeros(Pn), 0
+    for t in range(1, 4):
+        g = rng.randn(Pn)
+        ops.adam_step(td, out32, torch.tensor(g, dtype=torch.float64, device=dev), m, v, t)
+        th_o, m_o, v_o, t_o = P.adam_step(th_o, g, m_o, v_o, t_o)
+    np.testing.assert_allclose(td.cpu().numpy(), th_o, rtol=1e-12)
