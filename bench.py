@@ -1,0 +1,314 @@
+"""bench.py -- env-steps/s of one full BatchPolopt iteration (rollout + process_samples + policy update) on B200.
+
+Workload (BASELINE.json configs[1]): CartPoleEnv, 65 536 lanes per GPU, horizon 200, VPG + LinearFeatureBaseline,
+GaussianMLPPolicy(32,32).  One "step" = one training iteration = N*T env steps.
+  value  : device-resident iteration (policy parameters already in HBM), CUDA-event timed, max over ranks.
+  e2e    : the same iteration through the plugin API with HOST parameter buffers: policy.set_param_values(host) ->
+           algo.train_itr() -> policy.get_param_values() (+ the logged statistics and the baseline normal equations
+           read back), host<->device copies inside the timed region.
+  --impl reference : the reference's CPU sampler structure (oracle/cpu_sampler.py: per-path Python rollouts in a
+           process pool over all host cores + NumPy update) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (env, algo, lanes/GPU, horizon, hidden, alg bytes per env step (4*(O+3A+1)+1))
+    "cartpole_vpg_65536x200": ("cartpole", "vpg", 65536, 200, 32, 33),
+    "pendulum_vpg_262144x200": ("pendulum", "vpg", 262144, 200, 32, 29),
+    "swimmer_trpo_16384x500": ("swimmer", "trpo", 16384, 500, 32, 81),
+    "hopper_trpo_4096x500": ("hopper", "trpo", 4096, 500, 64, 121),
+    "point_trpo_65536x100": ("point", "trpo", 65536, 100, 32, 37),
+}
+
+
+def make_env(name):
+    from rllab_b200.envs.normalized_env import normalize
+    if name == "cartpole":
+        from rllab_b200.envs.box2d.cartpole_env import CartpoleEnv
+        return normalize(CartpoleEnv())
+    if name == "pendulum":
+        from rllab_b200.envs.gym_env import GymEnv
+        return normalize(GymEnv("Pendulum-v0"))
+    if name == "point":
+        from rllab_b200.envs.point_env import PointEnv
+        return normalize(PointEnv())
+    if name == "swimmer":
+        from rllab_b200.envs.mujoco.swimmer_env import SwimmerEnv
+        return normalize(SwimmerEnv())
+    if name == "hopper":
+        from rllab_b200.envs.mujoco.hopper_env import HopperEnv
+        return normalize(HopperEnv())
+    raise ValueError(name)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.idx = gpu_index
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return dict(sm_mhz=(statistics.median(sm) if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, sustained copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_arm(workload, steps, warmup, cores=None, sample_steps=None, seconds_budget=20.0):
+    """Reference CPU path (port): returns (env-steps/s, info)."""
+    import numpy as np
+    from oracle import cpu_sampler as C, policy as P, envs as E
+    env_name, algo, lanes, T, hidden, _ = WORKLOADS[workload]
+    cores = cores or os.cpu_count() or 1
+    e = E.make(env_name)
+    dims = P.Dims(e.O, (hidden, hidden), e.A)
+    theta = P.init_params(dims, np.random.RandomState(1))
+    sampler = C.CpuSampler(env_name, dims, cores, seed=1)
+    # size the bounded sample: one short calibration iteration, then ~seconds_budget/(steps+warmup) per step
+    if sample_steps is None:
+        th, co, ad, ns, sec, _ = C.run_iteration(sampler, theta, None, dims, algo, 2000 * cores, T)
+        rate = ns / max(sec, 1e-6)
+        per_step = max(2.0, seconds_budget / max(1, steps + warmup))
+        sample_steps = int(max(2000 * cores, min(rate * per_step, lanes * T)))
+    coeffs, adam = None, None
+    times, counts = [], []
+    for i in range(warmup + steps):
+        theta, coeffs, adam, ns, sec, avg_ret = C.run_iteration(sampler, theta, coeffs, dims, algo, sample_steps, T, adam)
+        if i >= warmup:
+            times.append(sec), counts.append(ns)
+    sampler.close()
+    value = sum(counts) / sum(times)
+    info = dict(value=value, unit="env-steps/s", cores=cores, kind="port",
+                sample="%d iterations of >=%d env steps each (whole paths, max_path_length %d) of %s; "
+                       "per-path Python rollouts in %d worker processes + NumPy %s update (oracle/cpu_sampler.py)" %
+                       (steps, sample_steps, T, workload, cores, algo.upper()))
+    return value, info, sum(times) / len(times) * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cartpole_vpg_65536x200", choices=sorted(WORKLOADS))
+    ap.add_argument("--lanes", type=int, default=None, help="lanes per GPU (default: the workload's)")
+    ap.add_argument("--horizon", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    env_name, algo_name, lanes, T, hidden, alg_bytes = WORKLOADS[args.workload]
+    lanes = args.lanes or lanes
+    T = args.horizon or T
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        value, info, ms = cpu_arm(args.workload, args.steps, args.warmup, seconds_budget=90.0)
+        line = dict(metric="env-steps/sec (full iteration: rollout + process_samples + %s update)" % algo_name.upper(),
+                    value=value, unit="env-steps/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                    data="synthetic", impl="reference",
+                    config=dict(workload=args.workload, env=env_name, algo=algo_name, hidden=[hidden, hidden],
+                                horizon=T, note="bounded sample on host cores"),
+                    cpu_baseline=info,
+                    e2e=dict(value=value, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0)
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    from rllab_b200 import _lib as L
+    from rllab_b200.algos.trpo import TRPO
+    from rllab_b200.algos.vpg import VPG
+    from rllab_b200.baselines.linear_feature_baseline import LinearFeatureBaseline
+    from rllab_b200.misc import logger
+    from rllab_b200.parallel import Comm
+    from rllab_b200.policies.gaussian_mlp_policy import GaussianMLPPolicy
+
+    L.load()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    comm = Comm()
+    logger.set_quiet(True)
+    np.random.seed(1)
+    env = make_env(env_name)
+    policy = GaussianMLPPolicy(env.spec, hidden_sizes=(hidden, hidden), seed=1)
+    baseline = LinearFeatureBaseline(env.spec)
+    n_total = lanes * world
+    kw = dict(env=env, policy=policy, baseline=baseline, batch_size=n_total * T, max_path_length=T, n_itr=10 ** 9,
+              discount=0.99, sampler_args=dict(n_envs=n_total, seed=1, comm=comm))
+    algo = VPG(**kw) if algo_name == "vpg" else TRPO(step_size=0.01, **kw)
+    algo.start_worker()
+    algo.init_opt()
+    steps_per_iter = n_total * T
+    dev = torch.device("cuda", local_rank)
+
+    def sync_all():
+        comm.barrier()
+        torch.cuda.synchronize()
+
+    def run(n, itr0, e2e):
+        """n iterations; returns elapsed ms on this rank (CUDA events on the launching stream)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        host_theta = policy.get_param_values()
+        sync_all()
+        ev0.record()
+        for i in range(n):
+            if e2e:
+                policy.set_param_values(host_theta)            # H2D: P float64 from host memory
+            algo.train_itr(itr0 + i)
+            if e2e:
+                host_theta = policy.get_param_values()         # D2H: P float64
+        ev1.record()
+        sync_all()
+        return ev0.elapsed_time(ev1)
+
+    itr = 0
+    run(args.warmup, itr, False)
+    itr += args.warmup
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    k0 = L.kernel_launches()
+    ms_dev = run(args.steps, itr, False)
+    launches = (L.kernel_launches() - k0) / args.steps
+    itr += args.steps
+    ms_e2e = run(args.steps, itr, True)
+    itr += args.steps
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    comm.all_reduce_max(t)
+    ms_dev, ms_e2e = (float(x) for x in t.cpu().numpy())
+
+    # ---- per-kernel timing of the same iteration (CUDA events around each library call), for the roofline
+    from rllab_b200 import ops
+    b = algo.sampler.batch
+    dims = policy.dims
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    g = torch.zeros(policy.n_params, dtype=torch.float64, device=dev)
+    out3 = torch.zeros(3, dtype=torch.float64, device=dev)
+    loss_kind = L.LOSS_VPG if algo_name == "vpg" else L.LOSS_TRPO
+    O, A = policy.obs_dim, policy.action_dim
+    samp_bytes = 4 * (O + 3 * A + 1)
+    kern = {}
+    kern["rollout"] = dict(ms=timed(lambda: ops.rollout(algo.sampler.env_kind, policy.theta32, hidden, hidden,
+                                                        policy.min_std, b, T, None, None, 1, 12345, algo.sampler.lane0)),
+                           bytes=alg_bytes * b.B, per_iter=1)
+    w = baseline.device_weights(b.O, dev)
+    kern["process_samples"] = dict(ms=timed(lambda: ops.process_samples(b, w, 0.99, 1.0)),
+                                   bytes=(4 * O + 4 + 1 + 2 + 12) * b.B, per_iter=1)
+    gram = torch.empty(((2 * O + 5) * (2 * O + 6) // 2,), dtype=torch.float64, device=dev)
+    kern["lfb_gram"] = dict(ms=timed(lambda: ops.lfb_gram(b, gram)), bytes=(4 * O + 2 + 4) * b.B, per_iter=1)
+    kern["loss_kl"] = dict(ms=timed(lambda: ops.loss_kl(loss_kind, policy.theta32, dims, policy.min_std, b,
+                                                        1.0 / b.B_global, out3)),
+                           bytes=samp_bytes * b.B, per_iter=2 if algo_name == "vpg" else 3)
+    kern["grad"] = dict(ms=timed(lambda: ops.grad(loss_kind, policy.theta32, dims, policy.min_std, b,
+                                                  1.0 / b.B_global, g)), bytes=samp_bytes * b.B, per_iter=1)
+    if algo_name == "trpo":
+        x = torch.randn(policy.n_params, dtype=torch.float64, device=dev)
+        Hx = torch.zeros_like(x)
+        kern["fvp"] = dict(ms=timed(lambda: ops.fvp(policy.theta32, dims, policy.min_std, b, x, 1.0 / b.B_global,
+                                                    1e-5, 1.0, Hx)), bytes=4 * O * b.B, per_iter=11)
+    for k, v in kern.items():
+        v["GBps"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+        v["share_of_step"] = v["ms"] * v["per_iter"] / (ms_dev / args.steps)
+    dom = max(kern, key=lambda k: kern[k]["ms"] * kern[k]["per_iter"])
+    peak, peak_src = measured_peaks()
+    roofline = dict(bound="hbm", kernel=dom, achieved=kern[dom]["GBps"], peak=peak, unit="GB/s",
+                    frac=kern[dom]["GBps"] / peak, traffic=None, peak_source=peak_src,
+                    algorithmic_bytes_per_launch=kern[dom]["bytes"], launch_ms=kern[dom]["ms"],
+                    note="per-kernel CUDA-event times of this run; the policy passes are FP32-issue bound, not HBM "
+                         "bound (DESIGN.md 'Rooflines')")
+    if rank != 0:
+        return
+    value = steps_per_iter * args.steps / (ms_dev * 1e-3)
+    e2e_value = steps_per_iter * args.steps / (ms_e2e * 1e-3)
+    d = 2 * O + 4
+    P_ = policy.n_params
+    line = dict(
+        metric="env-steps/sec (full iteration: rollout + process_samples + %s update)" % algo_name.upper(),
+        value=value, unit="env-steps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+        data="synthetic", impl="b200",
+        config=dict(workload=args.workload, env=env_name, algo=algo_name, lanes_per_gpu=lanes, horizon=T,
+                    hidden=[hidden, hidden], samples_per_step=steps_per_iter, parallelism="lanes sharded x%d" % world,
+                    l2="trajectory buffers (%.0f MB/GPU) exceed the 126 MB L2" % (b.B * (alg_bytes + 14) / 1e6)),
+        e2e=dict(value=e2e_value, unit="env-steps/s", ms_per_step=ms_e2e / args.steps,
+                 h2d_bytes_per_step=8 * P_ + 8 * d, d2h_bytes_per_step=8 * P_ + 8 * (16 + 4 + 3 * 3) + 8 * ((d + 1) * (d + 2) // 2)),
+        gpu_launches=launches, clocks=clk, roofline=roofline,
+        kernels={k: dict(ms=round(v["ms"], 4), GBps=round(v["GBps"], 1), per_iter=v["per_iter"],
+                         share_of_step=round(v["share_of_step"], 3)) for k, v in kern.items()},
+        stats=dict(AverageReturn=algo.sampler.stats.get("AverageReturn"), NumTrajs=algo.sampler.stats.get("NumTrajs")),
+    )
+    if world == 1 and not args.no_cpu_baseline:
+        _, info, _ = cpu_arm(args.workload, 2, 1, seconds_budget=args.cpu_seconds)
+        line["cpu_baseline"] = info
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

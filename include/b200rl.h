@@ -61,6 +61,8 @@ extern "C" {
 
 const char* b200rl_last_error(void);
 int b200rl_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py reports the per-step delta). */
+unsigned long long b200rl_kernel_launches(void);
 /* SM count of the current device (grid sizing helper for callers that size workspaces). */
 int b200rl_device_sms(int* sms_out);
 
@@ -84,11 +86,12 @@ int b200rl_fill_noise(float* out, int rows, int row0, int K, int N, long long la
 int b200rl_env_reset(int env_kind, int N, float* state, float* obs_out, const float* reset_raw,
                      unsigned int seed, unsigned int iter, int row, long long lane0, void* stream);
 
-/* Env.step for N lanes (rllab/envs/base.py:6-24 through NormalizedEnv.step, normalized_env.py:78-92).
- * actions [A][N] are the policy's raw actions.  Writes obs_out [O][N], rew_out [N], done_out [N]; state is
- * advanced in place (no auto-reset here: the caller decides, as vec_env_executor.py:14-26 does). */
-int b200rl_env_step(int env_kind, int N, float* state, const float* actions, float* obs_out, float* rew_out,
-                    unsigned char* done_out, void* stream);
+/* Env.step for N lanes (rllab/envs/base.py:6-24).  normalized != 0: actions [A][N] are the policy's raw actions and
+ * go through NormalizedEnv.step (normalized_env.py:78-92) first; normalized == 0: actions are handed to the wrapped
+ * env unchanged.  Writes obs_out [O][N], rew_out [N], done_out [N]; state is advanced in place (no auto-reset here:
+ * the caller decides, as vec_env_executor.py:14-26 does). */
+int b200rl_env_step(int env_kind, int N, int normalized, float* state, const float* actions, float* obs_out,
+                    float* rew_out, unsigned char* done_out, void* stream);
 
 /* GaussianMLPPolicy.get_actions (rllab/policies/gaussian_mlp_policy.py:132-137): obs [O][n] ->
  * act_out, mean_out [A][n], log_std_out [A] (after the min_std clamp).  eps [A][n] or NULL (Philox). */

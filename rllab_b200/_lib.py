@@ -25,13 +25,14 @@ _LL = c_longlong
 SIGNATURES = {
     "b200rl_last_error": (c_char_p, []),
     "b200rl_version": (c_int, []),
+    "b200rl_kernel_launches": (ctypes.c_ulonglong, []),
     "b200rl_device_sms": (c_int, [POINTER(c_int)]),
     "b200rl_env_info": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                 POINTER(c_float), POINTER(c_float)]),
     "b200rl_policy_num_params": (_LL, [c_int, c_int, c_int, c_int]),
     "b200rl_fill_noise": (c_int, [_P, c_int, c_int, c_int, c_int, _LL, c_int, c_uint, c_uint, c_int, _P]),
     "b200rl_env_reset": (c_int, [c_int, c_int, _P, _P, _P, c_uint, c_uint, c_int, _LL, _P]),
-    "b200rl_env_step": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "b200rl_env_step": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "b200rl_policy_get_actions": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, _P, _LL, _P, c_uint, c_uint, c_int,
                                           _LL, _P, _P, _P, _P]),
     "b200rl_rollout": (c_int, [c_int, _P, c_int, c_int, c_float, c_int, c_int, c_int, _P, _P, c_uint, c_uint, _LL,
@@ -102,6 +103,10 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     launch_count += 1
     check(rc, name)
+
+
+def kernel_launches():
+    return int(load().b200rl_kernel_launches())
 
 
 def env_info(kind):

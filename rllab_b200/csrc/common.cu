@@ -6,6 +6,7 @@
 namespace b200rl {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_kernel_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -73,6 +74,8 @@ int b200rl_device_sms(int* sms_out) {
   if (sms_out) *sms_out = sms;
   return 0;
 }
+
+unsigned long long b200rl_kernel_launches(void) { return b200rl::g_kernel_launches; }
 
 long long b200rl_ws_doubles(void) {
   return (long long)b200rl::MAX_PARTIAL_BLOCKS * b200rl::MAX_PARTIAL_K;

@@ -19,8 +19,11 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::b200rl::cuda_fail(_e, #expr); \
   } while (0)
 
+extern unsigned long long g_kernel_launches;  // every kernel launch of the library passes through LAUNCH_CHECK
+
 #define B200RL_LAUNCH_CHECK(name)                                 \
   do {                                                            \
+    ++::b200rl::g_kernel_launches;                                \
     cudaError_t _e = cudaGetLastError();                          \
     if (_e != cudaSuccess) return ::b200rl::cuda_fail(_e, name);  \
   } while (0)

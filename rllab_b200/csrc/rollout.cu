@@ -131,7 +131,7 @@ __global__ void env_reset_kernel(int N, float* __restrict__ state, float* __rest
 }
 
 template <class Env>
-__global__ void env_step_kernel(int N, float* __restrict__ state, const float* __restrict__ actions,
+__global__ void env_step_kernel(int N, int normalized, float* __restrict__ state, const float* __restrict__ actions,
                                 float* __restrict__ obs_out, float* __restrict__ rew_out,
                                 unsigned char* __restrict__ done_out) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,7 +140,10 @@ __global__ void env_step_kernel(int N, float* __restrict__ state, const float* _
 #pragma unroll
   for (int k = 0; k < Env::S; ++k) s[k] = state[(size_t)k * N + n];
 #pragma unroll
-  for (int k = 0; k < Env::A; ++k) u[k] = scale_action(actions[(size_t)k * N + n], Env::lb(k), Env::ub(k));
+  for (int k = 0; k < Env::A; ++k) {
+    const float a = actions[(size_t)k * N + n];
+    u[k] = normalized ? scale_action(a, Env::lb(k), Env::ub(k)) : a;
+  }
   float r;
   bool done;
   Env::step(s, u, r, done);
@@ -272,12 +275,12 @@ int b200rl_env_reset(int env_kind, int N, float* state, float* obs_out, const fl
   return 0;
 }
 
-int b200rl_env_step(int env_kind, int N, float* state, const float* actions, float* obs_out, float* rew_out,
-                    unsigned char* done_out, void* stream) {
+int b200rl_env_step(int env_kind, int N, int normalized, float* state, const float* actions, float* obs_out,
+                    float* rew_out, unsigned char* done_out, void* stream) {
   B200RL_REQUIRE(N > 0 && state && actions && obs_out && rew_out && done_out, "env_step: bad arguments");
   B200RL_DISPATCH_ENV(env_kind, {
-    env_step_kernel<Env><<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, state, actions, obs_out, rew_out,
-                                                                             done_out);
+    env_step_kernel<Env><<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, normalized, state, actions, obs_out,
+                                                                             rew_out, done_out);
   });
   B200RL_LAUNCH_CHECK("env_step_kernel");
   return 0;

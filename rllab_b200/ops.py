@@ -60,6 +60,9 @@ class LaneBatch(object):
         self.base = torch.empty((T, N), dtype=F32, device=device)
         self.sums = torch.zeros((L.PS_NSUM,), dtype=F64, device=device)
         self.maxs = torch.zeros((L.PS_NMAX,), dtype=F64, device=device)
+        self.version = 0              # bumped by the sampler whenever the contents change
+        self.processed = False        # adv/ret/base valid (process_samples has run on this rollout)
+        self.B_global = N * T         # samples over all ranks (the sampler overwrites it under torchrun)
 
     @property
     def B(self):
@@ -83,10 +86,10 @@ def env_reset(kind, N, state, obs_out, reset_raw=None, seed=0, it=0, row=0, lane
     L.call("b200rl_env_reset", kind, N, L.ptr(state), L.ptr(obs_out), L.ptr(reset_raw), seed, it, row, lane0, _stream())
 
 
-def env_step(kind, N, state, actions, obs_out, rew_out, done_out):
+def env_step(kind, N, state, actions, obs_out, rew_out, done_out, normalized=True):
     _chk(state, F32, "state"), _chk(actions, F32, "actions"), _chk(obs_out, F32, "obs_out")
     _chk(rew_out, F32, "rew_out", N), _chk(done_out, U8, "done_out", N)
-    L.call("b200rl_env_step", kind, N, L.ptr(state), L.ptr(actions), L.ptr(obs_out), L.ptr(rew_out), L.ptr(done_out),
+    L.call("b200rl_env_step", kind, N, int(bool(normalized)), L.ptr(state), L.ptr(actions), L.ptr(obs_out), L.ptr(rew_out), L.ptr(done_out),
            _stream())
 
 

@@ -1,0 +1,200 @@
+"""GPU: the plugin API (Env / Policy / Baseline / Sampler / BatchPolopt, TRPO and VPG) end to end, and the policy
+update against the CPU oracle on the very same batch: parameters within 1e-5 relative (north_star tolerance)."""
+import pickle
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import optim as OPT          # noqa: E402
+from oracle import policy as P           # noqa: E402
+from oracle import sampler as S          # noqa: E402
+
+PARAM_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rllab_b200 import _lib
+    _lib.load()
+    from rllab_b200.misc import logger
+    logger.set_quiet(True)
+    return torch.device("cuda:0")
+
+
+def _make(env_name):
+    import bench
+    return bench.make_env(env_name)
+
+
+def _algo(env_name, algo_name, n_envs, T, hidden=32, **kw):
+    from rllab_b200.algos.trpo import TRPO
+    from rllab_b200.algos.vpg import VPG
+    from rllab_b200.baselines.linear_feature_baseline import LinearFeatureBaseline
+    from rllab_b200.policies.gaussian_mlp_policy import GaussianMLPPolicy
+    env = _make(env_name)
+    policy = GaussianMLPPolicy(env.spec, hidden_sizes=(hidden, hidden), seed=3)
+    baseline = LinearFeatureBaseline(env.spec)
+    args = dict(env=env, policy=policy, baseline=baseline, batch_size=n_envs * T, max_path_length=T, n_itr=3,
+                discount=0.99, sampler_args=dict(n_envs=n_envs, seed=7))
+    args.update(kw)
+    return (TRPO(**args) if algo_name == "trpo" else VPG(**args))
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+@pytest.mark.parametrize("env_name,hidden", [("cartpole", 32), ("point", 32), ("pendulum", 32), ("cartpole", 64)])
+def test_trpo_update_matches_oracle(dev, env_name, hidden):
+    algo = _algo(env_name, "trpo", 1024, 50, hidden)
+    algo.start_worker()
+    algo.init_opt()
+    paths = algo.sampler.obtain_samples(0)
+    sd = algo.sampler.process_samples(0, paths)
+    b = sd.lane_batch
+    theta0 = algo.policy.theta32.double().cpu().numpy()
+    traj = b.to_numpy()
+    batch = S.batch_from_traj(traj, b.adv.cpu().numpy())
+    algo.optimize_policy(0, sd)
+    theta_dev = algo.policy.get_param_values()
+    dims = P.Dims(b.O, (hidden, hidden), b.A)
+    theta_ref, info = OPT.trpo_step(theta0, batch, dims, step_size=0.01)
+    li = algo.optimizer.last_info
+    assert li["n_iter"] == info["n_iter"] and li["rejected"] == info["rejected"]      # index work: identical
+    assert not info["rejected"]
+    assert _rel(theta_dev, theta_ref) < PARAM_RTOL, _rel(theta_dev, theta_ref)
+    np.testing.assert_allclose(li["loss_before"], info["loss_before"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(li["constraint_val"], info["constraint_val"], rtol=2e-4)
+    assert 0 < li["constraint_val"] <= 0.01
+
+
+@pytest.mark.parametrize("env_name", ["cartpole", "pendulum"])
+def test_vpg_updates_match_oracle(dev, env_name):
+    algo = _algo(env_name, "vpg", 1024, 50)
+    algo.start_worker()
+    algo.init_opt()
+    dims = None
+    adam = None
+    theta_ref = None
+    for itr in range(3):                      # Adam moments / step counter persist across iterations
+        paths = algo.sampler.obtain_samples(itr)
+        sd = algo.sampler.process_samples(itr, paths)
+        b = sd.lane_batch
+        if dims is None:
+            dims = P.Dims(b.O, (32, 32), b.A)
+            adam = (np.zeros(dims.P), np.zeros(dims.P), 0)
+        theta0 = algo.policy.get_param_values()
+        batch = S.batch_from_traj(b.to_numpy(), b.adv.cpu().numpy())
+        # the kernels see float32(theta); hand the oracle the same numbers
+        th32 = algo.policy.theta32.double().cpu().numpy()
+        g_ref = P.grad_surr(th32, batch, dims, "vpg")
+        theta_ref, m, v, t = P.adam_step(theta0, g_ref, adam[0], adam[1], adam[2])
+        adam = (m, v, t)
+        algo.optimize_policy(itr, sd)
+        theta_dev = algo.policy.get_param_values()
+        assert _rel(theta_dev, theta_ref) < PARAM_RTOL, (itr, _rel(theta_dev, theta_ref))
+        algo.policy.set_param_values(theta_ref)     # keep both sides on the same trajectory of parameters
+
+
+@pytest.mark.parametrize("algo_name", ["trpo", "vpg"])
+def test_train_loop_runs_and_logs(dev, algo_name):
+    """Mirror of the reference's integration smoke (tests/test_algos.py:28-94): a few iterations, no NaN params,
+    plus the tabular keys of sampler/base.py:170-180 and npo.py:118-122 / vpg.py:124-130."""
+    from rllab_b200.misc import logger
+    algo = _algo("cartpole", algo_name, 512, 100, n_itr=2)
+    algo.train()
+    assert not np.any(np.isnan(algo.policy.get_param_values()))
+    tab = logger.get_last_table()
+    keys = ["Iteration", "AverageDiscountedReturn", "AverageReturn", "ExplainedVariance", "NumTrajs", "Entropy",
+            "Perplexity", "StdReturn", "MaxReturn", "MinReturn", "AveragePolicyStd", "LossBefore", "LossAfter", "MeanKL"]
+    keys += ["MeanKLBefore", "dLoss"] if algo_name == "trpo" else ["MaxKL"]
+    for k in keys:
+        assert k in tab, k
+    assert tab["Iteration"] == 1 and tab["NumTrajs"] >= 512
+    assert abs(tab["Entropy"] - 1.41894) < 0.05          # docs/user/experiments.rst:88 at init (log_std ~ 0, A = 1)
+    assert algo.current_itr == 2
+
+
+def test_trpo_improves_cartpole_return(dev):
+    algo = _algo("cartpole", "trpo", 2048, 100, n_itr=12)
+    from rllab_b200.misc import logger
+    rets = []
+    algo.start_worker()
+    algo.init_opt()
+    for itr in range(12):
+        algo.train_itr(itr)
+        rets.append(logger.get_last_table()["AverageReturn"])
+    assert rets[-1] > 2.0 * rets[0], rets
+
+
+def test_samples_data_wire_format(dev):
+    algo = _algo("point", "trpo", 64, 30)
+    algo.start_worker()
+    algo.init_opt()
+    paths = algo.sampler.obtain_samples(0)
+    sd = algo.sampler.process_samples(0, paths)
+    b = sd.lane_batch
+    assert sd["observations"].shape == (b.B, 2) and sd["actions"].shape == (b.B, 2)
+    assert sd["advantages"].shape == (b.B,) and sd["agent_infos"]["mean"].shape == (b.B, 2)
+    np.testing.assert_array_equal(sd["observations"], b.obs.cpu().numpy().reshape(2, -1).T.astype(np.float64))
+    plist = sd["paths"]
+    assert sum(len(p["rewards"]) for p in plist) == b.B == 64 * 30
+    assert abs(sd["advantages"].mean()) < 1e-5 and abs(sd["advantages"].std() - 1) < 1e-3      # centered
+    p0 = plist[0]
+    assert set(p0) >= {"observations", "actions", "rewards", "agent_infos", "env_infos", "advantages", "returns"}
+    np.testing.assert_allclose(p0["returns"], S.discount_cumsum(p0["rewards"], 0.99), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("env_name", ["point", "cartpole", "pendulum"])
+def test_env_protocol(dev, env_name):
+    """tests/envs/test_envs.py:86-102: reset in obs space, action in action space, one step, scalar reward."""
+    env = _make(env_name)
+    ob_space, act_space = env.observation_space, env.action_space
+    ob = env.reset()
+    assert ob_space.contains(ob)
+    a = act_space.sample()
+    assert act_space.contains(a)
+    res = env.step(a)
+    assert ob_space.contains(res.observation) and np.isscalar(res.reward) and isinstance(res.done, bool)
+    inner = env.wrapped_env
+    lb, ub = inner.action_space.bounds
+    inner.reset()
+    r2 = inner.step(np.clip(lb + (a + 1.) * 0.5 * (ub - lb), lb, ub))     # un-normalised env takes wrapped-space actions
+    assert ob_space.contains(r2.observation)
+    env.terminate()
+
+
+def test_vec_env_executor_semantics(dev):
+    """sandbox/rocky/tf/envs/vec_env_executor.py:14-26: horizon cut and auto-reset."""
+    env = _make("cartpole")
+    vec = env.vec_env_executor(n_envs=16, max_path_length=5)
+    obs = vec.reset()
+    assert np.asarray(obs).shape == (16, 4) and vec.num_envs == 16
+    for t in range(5):
+        obs, rew, dones, infos = vec.step(np.zeros((16, 1)))
+    assert dones.all() and (vec.ts == 0).all()               # every lane hit max_path_length on the 5th step
+    assert np.all(np.abs(obs[:, 0]) <= 0.12 + 1e-6)           # returned obs is the reset obs (cartpole_env.py:31-42)
+
+
+def test_policy_api_and_pickle(dev):
+    from rllab_b200.policies.gaussian_mlp_policy import GaussianMLPPolicy
+    env = _make("cartpole")
+    pol = GaussianMLPPolicy(env.spec, seed=0)
+    flat = pol.get_param_values()
+    assert flat.shape == (1250,) and flat.dtype == np.float64
+    a, info = pol.get_action(env.reset())
+    assert a.shape == (1,) and set(info) == {"mean", "log_std"}
+    acts, infos = pol.get_actions(np.zeros((7, 4)))
+    assert acts.shape == (7, 1) and infos["mean"].shape == (7, 1) and np.allclose(infos["log_std"], 0.0)
+    mu, _ = P.forward(pol.theta32.double().cpu().numpy(), np.zeros((7, 4)), P.Dims(4, (32, 32), 1))
+    np.testing.assert_allclose(infos["mean"], mu, rtol=1e-5, atol=1e-6)
+    pol.set_param_values(flat * 0.5)
+    np.testing.assert_array_equal(pol.get_param_values(), flat * 0.5)
+    pol2 = pickle.loads(pickle.dumps(pol))
+    np.testing.assert_array_equal(pol2.get_param_values(), flat * 0.5)
+    assert pol.distribution.entropy(dict(log_std=np.zeros((1, 1))))[0] == pytest.approx(1.41894, abs=1e-5)
