@@ -28,13 +28,13 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 
 // Dense layer, thread-per-sample, weights W [NIN][NOUT] row-major + bias in shared memory (broadcast LDS.128).
 // Output pairs (j, j+1) share one packed FFMA2; even and odd inputs accumulate in separate chains (canonical order).
-template <int NIN, int NOUT>
+template <int NIN, int NOUT, bool BIAS = true>
 __device__ __forceinline__ void dense_thread(const float* __restrict__ W, const float* __restrict__ b,
                                              const float (&in)[NIN], float (&pre)[NOUT]) {
   float2 ae[NOUT / 2], ao[NOUT / 2];
 #pragma unroll
   for (int j = 0; j < NOUT; j += 4) {
-    float4 bb = *reinterpret_cast<const float4*>(b + j);
+    float4 bb = BIAS ? *reinterpret_cast<const float4*>(b + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     ae[j / 2] = make_float2(bb.x, bb.y);
     ae[j / 2 + 1] = make_float2(bb.z, bb.w);
     ao[j / 2] = make_float2(0.f, 0.f);
@@ -93,6 +93,17 @@ __device__ __forceinline__ float clamp_log_std(float param, float log_min_std) {
     using NetT = ::b200rl::Net<O_, H_, H_, A_>;                                              \
     __VA_ARGS__;                                                                             \
   } else
+
+#define B200RL_DISPATCH_NET_H(H_, ...)                                                       \
+  B200RL_DISPATCH_NET_OA(2, 2, H_, __VA_ARGS__)                                              \
+  B200RL_DISPATCH_NET_OA(4, 1, H_, __VA_ARGS__)                                              \
+  B200RL_DISPATCH_NET_OA(3, 1, H_, __VA_ARGS__)                                              \
+  B200RL_DISPATCH_NET_OA(13, 2, H_, __VA_ARGS__)                                             \
+  B200RL_DISPATCH_NET_OA(20, 3, H_, __VA_ARGS__)                                             \
+  {                                                                                          \
+    ::b200rl::set_error("network shape O=%d A=%d hidden=(%d,%d) is not compiled in", obs_dim, act_dim, h1, h2); \
+    return B200RL_EUNSUPPORTED;                                                              \
+  }
 
 #define B200RL_DISPATCH_NET(...)                                                             \
   B200RL_DISPATCH_NET_OA(2, 2, 32, __VA_ARGS__)                                              \

@@ -8,25 +8,14 @@
 // f_loss_constraint), :22-55 (PerlmutterHvp f_Hx_plain), rllab/optimizers/first_order_optimizer.py:62-76 (grad part
 // of f_opt), rllab/algos/vpg.py:100-103 (f_kl), over rllab/algos/npo.py:72-82 / vpg.py:88-99 and
 // rllab/distributions/diagonal_gaussian.py:14-34,58-69.
-#include "mlp.cuh"
+#include "update_common.cuh"
 
 namespace b200rl {
 
 constexpr int UPD_WARPS = 4;
 constexpr int UPD_THREADS = UPD_WARPS * 32;
-constexpr int MODE_LOSS = 0, MODE_GRAD = 1, MODE_FVP = 2;
 constexpr int FLUSH_GROUPS = 4;  // float32 register accumulators are folded into float64 every 4*32 samples
 
-struct UpdArgs {
-  const float* params;
-  const double* xvec;  // FVP: tangent vector (float64, P)
-  float log_min_std;
-  long long B;
-  const float *obs, *act, *adv, *old_mean, *old_log_std;
-  int loss_kind;
-  int unit_half;  // 64-wide nets: which half of the layer-2 units accumulates dW1 in this pass (0/1)
-  double* partial;
-};
 
 template <class N, int MODE>
 struct UpdSmem {
@@ -402,6 +391,72 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
   }
 }
 
+// Surrogate loss + KL, one THREAD per sample (forward only: no cross-sample reduction of per-weight quantities, so
+// the thread-per-lane forward of the rollout kernel is the cheapest formulation; same canonical summation order).
+constexpr int LOSS_THREADS = 128;
+template <class N>
+__global__ void __launch_bounds__(LOSS_THREADS) loss_thread_kernel(UpdArgs a) {
+  constexpr int O = N::O, A = N::A;
+  __shared__ __align__(16) float sp[N::P];
+  __shared__ double red_scratch[3 * 32];
+  for (int i = threadIdx.x; i < N::P; i += blockDim.x) sp[i] = a.params[i];
+  __syncthreads();
+  float ls_new[A], inv_std[A], var_new[A], var_new2[A], ls_old[A], inv_std_old[A], var_old[A];
+  float sum_ls_new = 0.f, sum_ls_old = 0.f;
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    ls_new[k] = clamp_log_std(sp[N::ols + k], a.log_min_std);
+    const float sd = expf(ls_new[k]);
+    inv_std[k] = 1.0f / sd;
+    var_new[k] = sd * sd;
+    var_new2[k] = 2.0f * sd * sd + 1e-8f;
+    ls_old[k] = a.old_log_std[k];
+    const float so = expf(ls_old[k]);
+    inv_std_old[k] = 1.0f / so;
+    var_old[k] = so * so;
+    sum_ls_new += ls_new[k];
+    sum_ls_old += ls_old[k];
+  }
+  const float half_log2pi_A = 0.5f * (float)A * 1.8378770664093453f;
+  double s_loss = 0.0, s_kl = 0.0, m_kl = -1.0e300;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < a.B; s += stride) {
+    asm volatile("" ::: "memory");
+    float x[O], h1[N::H1], h2[N::H2], mu[A];
+#pragma unroll
+    for (int o = 0; o < O; ++o) x[o] = a.obs[(size_t)o * a.B + s];
+    mlp_forward_thread<N>(sp, x, h1, h2, mu);
+    float zsq = 0.f, zsq_old = 0.f, kl = 0.f;
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+      const float act = a.act[(size_t)k * a.B + s];
+      const float om = a.old_mean[(size_t)k * a.B + s];
+      const float z = (act - mu[k]) * inv_std[k];
+      zsq += z * z;
+      const float zo = (act - om) * inv_std_old[k];
+      zsq_old += zo * zo;
+      const float dm = om - mu[k];
+      kl += (dm * dm + var_old[k] - var_new[k]) / var_new2[k] + ls_new[k] - ls_old[k];
+    }
+    const float adv_s = a.adv[s];
+    const float logp_new = -sum_ls_new - 0.5f * zsq - half_log2pi_A;
+    float term;
+    if (a.loss_kind == B200RL_LOSS_TRPO) {
+      const float logp_old = -sum_ls_old - 0.5f * zsq_old - half_log2pi_A;
+      term = -expf(logp_new - logp_old) * adv_s;
+    } else {
+      term = -logp_new * adv_s;
+    }
+    s_loss += (double)term;
+    s_kl += (double)kl;
+    m_kl = fmax(m_kl, (double)kl);
+  }
+  double v[2] = {s_loss, s_kl};
+  double mx[1] = {m_kl};
+  block_reduce_store<2, false>(v, red_scratch, a.partial + (size_t)blockIdx.x * 3);
+  block_reduce_store<1, true>(mx, red_scratch, a.partial + (size_t)blockIdx.x * 3 + 2);
+}
+
 // Hx += diag_scale * (reg * x  (+)  M_l x_l on the un-clamped log_std entries)
 __global__ void fvp_diag_kernel(int P, int ols, int A, const float* __restrict__ params, float log_min_std,
                                 const double* __restrict__ x, double reg, double diag_scale, double* __restrict__ Hx) {
@@ -473,11 +528,15 @@ int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, 
   a.obs = obs; a.act = act; a.adv = adv; a.old_mean = old_mean; a.old_log_std = old_log_std;
   a.loss_kind = loss_kind; a.partial = ws;
   int grid = 0;
-  B200RL_DISPATCH_NET({
-    grid = update_grid<NetT, MODE_LOSS>(B);
-    int rc = launch_update<NetT, MODE_LOSS>(a, grid, st);
-    if (rc) return rc;
-  });
+  {
+    long long g = (long long)num_sms() * 4;
+    const long long need = (B + LOSS_THREADS - 1) / LOSS_THREADS;
+    if (g > need) g = need;
+    if (g > MAX_PARTIAL_BLOCKS) g = MAX_PARTIAL_BLOCKS;
+    grid = (int)g;
+  }
+  B200RL_DISPATCH_NET({ loss_thread_kernel<NetT><<<grid, LOSS_THREADS, 0, st>>>(a); });
+  B200RL_LAUNCH_CHECK("loss_thread_kernel");
   // partial layout [grid][3] = (sum loss, sum kl, max kl): strided finalize
   int rc = launch_finalize_sum(ws, grid, 3, out, scale, st);  // out[2] is overwritten below
   if (rc) return rc;
@@ -502,29 +561,36 @@ int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int
   a.obs = obs; a.act = act; a.adv = adv; a.old_mean = old_mean; a.old_log_std = old_log_std;
   a.loss_kind = loss_kind; a.partial = ws;
   int grid = 0, P = 0, ols = 0;
-  B200RL_DISPATCH_NET({
-    grid = update_grid<NetT, MODE_GRAD>(B);
-    P = NetT::P; ols = NetT::ols;
-    constexpr int U = NetT::H1 / 32;
-    for (int half = 0; half < U; ++half) {
-      a.unit_half = half;
-      // 64-wide nets: the second pass recomputes everything but only its dW1 half differs; both passes write the
-      // full vector, the halves are merged below.
-      a.partial = ws + (size_t)half * ((size_t)grid * (NetT::P + 3));
-      int rc = launch_update<NetT, MODE_GRAD>(a, grid, st);
-      if (rc) return rc;
-      rc = launch_finalize_sum(a.partial, grid, NetT::P, half == 0 ? g_out : ws + 2 * ((size_t)grid * (NetT::P + 3)),
-                               scale, st);
-      if (rc) return rc;
-    }
-    if (U == 2) {
-      // take dW1 columns 32..63 from the second pass
-      const double* g2 = ws + 2 * ((size_t)grid * (NetT::P + 3));
-      B200RL_CUDA_CHECK(cudaMemcpy2DAsync(g_out + NetT::oW1 + 32, NetT::H2 * sizeof(double), g2 + NetT::oW1 + 32,
-                                          NetT::H2 * sizeof(double), 32 * sizeof(double), NetT::H1,
-                                          cudaMemcpyDeviceToDevice, st));
-    }
-  });
+  if (h1 == 32 && h2 == 32) {
+    int rc = update_tile_launch(MODE_GRAD, obs_dim, act_dim, a, &grid, &P, &ols, st);
+    if (rc) return rc;
+    rc = launch_finalize_sum(ws, grid, P, g_out, scale, st);
+    if (rc) return rc;
+  } else {
+    B200RL_DISPATCH_NET_H(64, {
+      grid = update_grid<NetT, MODE_GRAD>(B);
+      P = NetT::P; ols = NetT::ols;
+      constexpr int U = NetT::H1 / 32;
+      for (int half = 0; half < U; ++half) {
+        a.unit_half = half;
+        // 64-wide nets: the second pass recomputes everything but only its dW1 half differs; both passes write the
+        // full vector, the halves are merged below.
+        a.partial = ws + (size_t)half * ((size_t)grid * (NetT::P + 3));
+        int rc = launch_update<NetT, MODE_GRAD>(a, grid, st);
+        if (rc) return rc;
+        rc = launch_finalize_sum(a.partial, grid, NetT::P,
+                                 half == 0 ? g_out : ws + 2 * ((size_t)grid * (NetT::P + 3)), scale, st);
+        if (rc) return rc;
+      }
+      if (U == 2) {
+        // take dW1 columns 32..63 from the second pass
+        const double* g2 = ws + 2 * ((size_t)grid * (NetT::P + 3));
+        B200RL_CUDA_CHECK(cudaMemcpy2DAsync(g_out + NetT::oW1 + 32, NetT::H2 * sizeof(double), g2 + NetT::oW1 + 32,
+                                            NetT::H2 * sizeof(double), 32 * sizeof(double), NetT::H1,
+                                            cudaMemcpyDeviceToDevice, st));
+      }
+    });
+  }
   mask_logstd_grad_kernel<<<1, 32, 0, st>>>(ols, act_dim, params_f32, a.log_min_std, g_out);
   B200RL_LAUNCH_CHECK("mask_logstd_grad_kernel");
   (void)P;
@@ -540,26 +606,33 @@ int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim
   a.params = params_f32; a.xvec = x; a.log_min_std = min_std > 0.f ? logf(min_std) : -INFINITY; a.B = B;
   a.obs = obs; a.partial = ws;
   int grid = 0, P = 0, ols = 0;
-  B200RL_DISPATCH_NET({
-    grid = update_grid<NetT, MODE_FVP>(B);
-    P = NetT::P; ols = NetT::ols;
-    constexpr int U = NetT::H1 / 32;
-    for (int half = 0; half < U; ++half) {
-      a.unit_half = half;
-      a.partial = ws + (size_t)half * ((size_t)grid * NetT::P);
-      int rc = launch_update<NetT, MODE_FVP>(a, grid, st);
-      if (rc) return rc;
-      rc = launch_finalize_sum(a.partial, grid, NetT::P, half == 0 ? Hx_out : ws + 2 * ((size_t)grid * NetT::P), scale,
-                               st);
-      if (rc) return rc;
-    }
-    if (U == 2) {
-      const double* g2 = ws + 2 * ((size_t)grid * NetT::P);
-      B200RL_CUDA_CHECK(cudaMemcpy2DAsync(Hx_out + NetT::oW1 + 32, NetT::H2 * sizeof(double), g2 + NetT::oW1 + 32,
-                                          NetT::H2 * sizeof(double), 32 * sizeof(double), NetT::H1,
-                                          cudaMemcpyDeviceToDevice, st));
-    }
-  });
+  if (h1 == 32 && h2 == 32) {
+    int rc = update_tile_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st);
+    if (rc) return rc;
+    rc = launch_finalize_sum(ws, grid, P, Hx_out, scale, st);
+    if (rc) return rc;
+  } else {
+    B200RL_DISPATCH_NET_H(64, {
+      grid = update_grid<NetT, MODE_FVP>(B);
+      P = NetT::P; ols = NetT::ols;
+      constexpr int U = NetT::H1 / 32;
+      for (int half = 0; half < U; ++half) {
+        a.unit_half = half;
+        a.partial = ws + (size_t)half * ((size_t)grid * NetT::P);
+        int rc = launch_update<NetT, MODE_FVP>(a, grid, st);
+        if (rc) return rc;
+        rc = launch_finalize_sum(a.partial, grid, NetT::P, half == 0 ? Hx_out : ws + 2 * ((size_t)grid * NetT::P),
+                                 scale, st);
+        if (rc) return rc;
+      }
+      if (U == 2) {
+        const double* g2 = ws + 2 * ((size_t)grid * NetT::P);
+        B200RL_CUDA_CHECK(cudaMemcpy2DAsync(Hx_out + NetT::oW1 + 32, NetT::H2 * sizeof(double), g2 + NetT::oW1 + 32,
+                                            NetT::H2 * sizeof(double), 32 * sizeof(double), NetT::H1,
+                                            cudaMemcpyDeviceToDevice, st));
+      }
+    });
+  }
   // the log_std slot of the sample sum is zero (mean does not depend on log_std); add reg*x and the M_l block
   fvp_diag_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, ols, act_dim, params_f32, a.log_min_std, x, reg_coeff,
                                                    diag_scale, Hx_out);

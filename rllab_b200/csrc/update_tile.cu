@@ -1,0 +1,343 @@
+// Surrogate gradient and Fisher-vector product for 32-wide policies: one THREAD per sample for the per-sample math
+// (forward, tangent-forward, backward -- the same canonical summation order as the rollout kernel), then a
+// block-cooperative accumulation of the weight gradients as small Gram products over a 128-sample tile staged in
+// shared memory:
+//     dW0 = X^T D1, db0 = 1^T D1, dW1 = H1^T D2, db1 = 1^T D2, dWout = H2^T DM, dbout = 1^T DM, dlog_std = 1^T DL
+// dW1 (32x32 outputs, the bulk) uses 4x4 register tiles, rows interleaved by 8 so that every LDS.128 of a warp is
+// conflict-free (one wavefront), split in two K-halves over the 128 threads; per-tile float32 partial products are
+// folded into float64 register accumulators; per-block float64 partials are reduced in fixed order by the caller.
+//
+// Replaces f_grad / f_Hx_plain of rllab/optimizers/conjugate_gradient_optimizer.py:184-215,22-55 and the gradient
+// half of f_opt in rllab/optimizers/first_order_optimizer.py:62-76.
+#include "update_common.cuh"
+
+namespace b200rl {
+
+constexpr int T_THREADS = 128, T_TILE = 128, T_LD = T_TILE + 4;
+
+template <class N, int MODE>
+struct TileSmem {
+  static constexpr int O = N::O, H = N::H1, A = N::A;
+  static_assert(N::H1 == 32 && N::H2 == 32, "tile kernel is specialised for 32-wide layers");
+  static constexpr int rX = 0, rH1 = rX + O, rH2 = rH1 + H, rD1 = rH2 + H, rD2 = rD1 + H, rDM = rD2 + H, rDL = rDM + A,
+                       R = rDL + A;
+  static constexpr int P4 = (N::P + 3) & ~3;
+  static constexpr int o_sp = 0, o_sv = P4, o_stage = (MODE == MODE_FVP ? 2 : 1) * P4;
+  static constexpr int n_floats = o_stage + R * T_LD;
+  static constexpr int scratch_off = ((n_floats * 4 + 15) / 16) * 16;
+  static constexpr size_t bytes = (size_t)scratch_off + 3 * 32 * 8;
+  static_assert(2 * 64 * 16 * 8 <= R * T_LD * 4, "stage region must hold the K-half combine scratch");
+};
+
+template <class N, int MODE>
+__global__ void __launch_bounds__(T_THREADS) update_tile_kernel(UpdArgs a) {
+  using SM = TileSmem<N, MODE>;
+  constexpr int O = N::O, H = 32, A = N::A, P = N::P, LD = T_LD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sf = reinterpret_cast<float*>(smem_raw);
+  float* sp = sf + SM::o_sp;
+  float* sv = sf + SM::o_sv;
+  float* stage = sf + SM::o_stage;
+  double* red_scratch = reinterpret_cast<double*>(smem_raw + SM::scratch_off);
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < P; i += T_THREADS) sp[i] = a.params[i];
+  if constexpr (MODE == MODE_FVP)
+    for (int i = tid; i < P; i += T_THREADS) sv[i] = (float)a.xvec[i];
+  __syncthreads();
+
+  // distribution constants
+  float ls_new[A], inv_std[A], ls_old[A], inv_std_old[A], Mmu[A];
+  float sum_ls_new = 0.f, sum_ls_old = 0.f;
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    ls_new[k] = clamp_log_std(sp[N::ols + k], a.log_min_std);
+    const float sd = expf(ls_new[k]);
+    inv_std[k] = 1.0f / sd;
+    Mmu[k] = 2.0f / (2.0f * sd * sd + 1e-8f);
+    ls_old[k] = (MODE == MODE_FVP) ? ls_new[k] : a.old_log_std[k];
+    inv_std_old[k] = 1.0f / expf(ls_old[k]);
+    sum_ls_new += ls_new[k];
+    sum_ls_old += ls_old[k];
+  }
+  const float half_log2pi_A = 0.5f * (float)A * 1.8378770664093453f;
+
+  // ---- Gram ownership
+  const int w1_tile = tid & 63, kh = tid >> 6;
+  const int ti = w1_tile >> 3, tj = w1_tile & 7;
+  double accW1[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) accW1[r][c] = 0.0;
+  constexpr int NS = (O + 1 > A + 1) ? O + 1 : A + 1;
+  double accS[NS];   // small-output accumulators of this thread's task (see below)
+#pragma unroll
+  for (int k = 0; k < NS; ++k) accS[k] = 0.0;
+  double s_loss = 0.0;
+
+  const long long ntiles = (a.B + T_TILE - 1) / T_TILE;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    asm volatile("" ::: "memory");
+    const long long s = tile * T_TILE + tid;
+    const bool valid = s < a.B;
+    // ================= phase A: per-sample forward / (tangent) / backward, staged to shared memory
+    {
+      float x[O], h1[H], h2[H], d2[H], dmu[A];
+      const long long sl = valid ? s : a.B - 1;
+#pragma unroll
+      for (int o = 0; o < O; ++o) x[o] = a.obs[(size_t)o * a.B + sl];
+      dense_thread<O, H>(sp + N::oW0, sp + N::ob0, x, h1);
+#pragma unroll
+      for (int j = 0; j < H; ++j) h1[j] = tanh_f(h1[j]);
+      dense_thread<H, H>(sp + N::oW1, sp + N::ob1, h1, h2);
+      asm volatile("" ::: "memory");   // do not keep shared-memory weights live in registers across sections
+#pragma unroll
+      for (int j = 0; j < H; ++j) h2[j] = tanh_f(h2[j]);
+      if constexpr (MODE == MODE_GRAD) {
+        float mu[A];
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          float s0 = sp[N::obo + k], s1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < H; j += 2) {
+            s0 = fmaf(h2[j], sp[N::oWo + j * A + k], s0);
+            s1 = fmaf(h2[j + 1], sp[N::oWo + (j + 1) * A + k], s1);
+          }
+          mu[k] = s0 + s1;
+        }
+        float z[A], zsq = 0.f, zsq_old = 0.f;
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          const float act = a.act[(size_t)k * a.B + sl];
+          const float om = a.old_mean[(size_t)k * a.B + sl];
+          z[k] = (act - mu[k]) * inv_std[k];
+          zsq += z[k] * z[k];
+          const float zo = (act - om) * inv_std_old[k];
+          zsq_old += zo * zo;
+        }
+        const float adv_s = a.adv[sl];
+        const float logp_new = -sum_ls_new - 0.5f * zsq - half_log2pi_A;
+        float w_s, term;
+        if (a.loss_kind == B200RL_LOSS_TRPO) {
+          const float logp_old = -sum_ls_old - 0.5f * zsq_old - half_log2pi_A;
+          w_s = expf(logp_new - logp_old) * adv_s;
+          term = -w_s;
+        } else {
+          w_s = adv_s;
+          term = -logp_new * adv_s;
+        }
+        if (!valid) { w_s = 0.f; term = 0.f; }
+        s_loss += (double)term;
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          dmu[k] = -w_s * z[k] * inv_std[k];
+          stage[(SM::rDM + k) * LD + tid] = dmu[k];
+          stage[(SM::rDL + k) * LD + tid] = -w_s * (z[k] * z[k] - 1.0f);
+        }
+      } else {
+        // tangent forward J x (x = sv): t1 = (1-h1^2)(x V0 + vb0); t2 = (1-h2^2)(t1 W1 + h1 V1 + vb1)
+        float t1[H], t2[H], p2b[H];
+        asm volatile("" ::: "memory");   // do not keep shared-memory weights live in registers across sections
+        dense_thread<O, H>(sv + N::oW0, sv + N::ob0, x, t1);
+#pragma unroll
+        for (int j = 0; j < H; ++j) t1[j] *= (1.0f - h1[j] * h1[j]);
+        dense_thread<H, H>(sp + N::oW1, sv + N::ob1, t1, t2);
+        asm volatile("" ::: "memory");   // do not keep shared-memory weights live in registers across sections
+        dense_thread<H, H, false>(sv + N::oW1, nullptr, h1, p2b);
+#pragma unroll
+        for (int j = 0; j < H; ++j) t2[j] = (t2[j] + p2b[j]) * (1.0f - h2[j] * h2[j]);
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          float s0 = sv[N::obo + k], s1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            s0 = fmaf(t2[j], sp[N::oWo + j * A + k], s0);
+            s1 = fmaf(h2[j], sv[N::oWo + j * A + k], s1);
+          }
+          dmu[k] = valid ? (s0 + s1) * Mmu[k] : 0.f;
+          stage[(SM::rDM + k) * LD + tid] = dmu[k];
+          stage[(SM::rDL + k) * LD + tid] = 0.f;
+        }
+      }
+      asm volatile("" ::: "memory");   // do not keep shared-memory weights live in registers across sections
+      // backward: d2 = (dmu Wout^T) (1-h2^2); d1 = (d2 W1^T) (1-h1^2)
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int k = 0; k < A; ++k) sacc = fmaf(dmu[k], sp[N::oWo + j * A + k], sacc);
+        d2[j] = sacc * (1.0f - h2[j] * h2[j]);
+        stage[(SM::rH2 + j) * LD + tid] = h2[j];
+        stage[(SM::rD2 + j) * LD + tid] = d2[j];
+      }
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < H; j += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(sp + N::oW1 + i * H + j);
+          acc = ffma2(make_float2(d2[j], d2[j + 1]), make_float2(w.x, w.y), acc);
+          acc = ffma2(make_float2(d2[j + 2], d2[j + 3]), make_float2(w.z, w.w), acc);
+        }
+        stage[(SM::rH1 + i) * LD + tid] = h1[i];
+        stage[(SM::rD1 + i) * LD + tid] = (acc.x + acc.y) * (1.0f - h1[i] * h1[i]);
+      }
+#pragma unroll
+      for (int o = 0; o < O; ++o) stage[(SM::rX + o) * LD + tid] = x[o];
+    }
+    __syncthreads();
+    // ================= phase B: Gram accumulation over the tile
+    {
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+      const float* U = stage + (SM::rH1 + ti) * LD + kh * 64;
+      const float* V = stage + (SM::rD2 + tj) * LD + kh * 64;
+#pragma unroll 4
+      for (int k = 0; k < 64; k += 4) {
+        float4 u[4], v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) u[r] = *reinterpret_cast<const float4*>(U + r * 8 * LD + k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(V + c * 8 * LD + k);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            acc[r][c] = fmaf(u[r].x, v[c].x, acc[r][c]);
+            acc[r][c] = fmaf(u[r].y, v[c].y, acc[r][c]);
+            acc[r][c] = fmaf(u[r].z, v[c].z, acc[r][c]);
+            acc[r][c] = fmaf(u[r].w, v[c].w, acc[r][c]);
+          }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) accW1[r][c] += (double)acc[r][c];
+      // small outputs: warp 0 -> (dW0[:,j], db0[j]); warp 1 -> (dWout[j,:], db1[j]); warp 2 lanes < 2A -> dbout / dlog_std
+      if (tid < 32) {
+        float sa[O + 1];
+#pragma unroll
+        for (int o = 0; o <= O; ++o) sa[o] = 0.f;
+        const float* D = stage + (SM::rD1 + tid) * LD;
+#pragma unroll 4
+        for (int k = 0; k < T_TILE; k += 4) {
+          const float4 d = *reinterpret_cast<const float4*>(D + k);
+#pragma unroll
+          for (int o = 0; o < O; ++o) {
+            const float4 xv = *reinterpret_cast<const float4*>(stage + (SM::rX + o) * LD + k);
+            sa[o] = fmaf(xv.x, d.x, sa[o]); sa[o] = fmaf(xv.y, d.y, sa[o]);
+            sa[o] = fmaf(xv.z, d.z, sa[o]); sa[o] = fmaf(xv.w, d.w, sa[o]);
+          }
+          sa[O] += (d.x + d.y) + (d.z + d.w);
+        }
+#pragma unroll
+        for (int o = 0; o <= O; ++o) accS[o] += (double)sa[o];
+      } else if (tid < 64) {
+        const int j = tid - 32;
+        float sa[A + 1];
+#pragma unroll
+        for (int k = 0; k <= A; ++k) sa[k] = 0.f;
+        const float* Hh = stage + (SM::rH2 + j) * LD;
+        const float* D = stage + (SM::rD2 + j) * LD;
+#pragma unroll 4
+        for (int k = 0; k < T_TILE; k += 4) {
+          const float4 hv = *reinterpret_cast<const float4*>(Hh + k);
+          const float4 d = *reinterpret_cast<const float4*>(D + k);
+#pragma unroll
+          for (int q = 0; q < A; ++q) {
+            const float4 m = *reinterpret_cast<const float4*>(stage + (SM::rDM + q) * LD + k);
+            sa[q] = fmaf(hv.x, m.x, sa[q]); sa[q] = fmaf(hv.y, m.y, sa[q]);
+            sa[q] = fmaf(hv.z, m.z, sa[q]); sa[q] = fmaf(hv.w, m.w, sa[q]);
+          }
+          sa[A] += (d.x + d.y) + (d.z + d.w);
+        }
+#pragma unroll
+        for (int k = 0; k <= A; ++k) accS[k] += (double)sa[k];
+      } else if (tid < 64 + 2 * A) {
+        const float* D = stage + (SM::rDM + (tid - 64)) * LD;   // rows DM[0..A-1], DL[0..A-1] are contiguous
+        float s0 = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < T_TILE; k += 4) {
+          const float4 d = *reinterpret_cast<const float4*>(D + k);
+          s0 += (d.x + d.y) + (d.z + d.w);
+        }
+        accS[0] += (double)s0;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ================= write this block's partial vector (float64)
+  double* out = a.partial + (size_t)blockIdx.x * P;
+  double* scr = reinterpret_cast<double*>(stage);   // [2][64][16]
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) scr[(kh * 64 + w1_tile) * 16 + r * 4 + c] = accW1[r][c];
+  __syncthreads();
+  if (tid < 64) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        out[N::oW1 + (ti + 8 * r) * H + (tj + 8 * c)] = scr[w1_tile * 16 + r * 4 + c] + scr[(64 + w1_tile) * 16 + r * 4 + c];
+  }
+  if (tid < 32) {
+#pragma unroll
+    for (int o = 0; o < O; ++o) out[N::oW0 + o * H + tid] = accS[o];
+    out[N::ob0 + tid] = accS[O];
+  } else if (tid < 64) {
+    const int j = tid - 32;
+#pragma unroll
+    for (int k = 0; k < A; ++k) out[N::oWo + j * A + k] = accS[k];
+    out[N::ob1 + j] = accS[A];
+  } else if (tid < 64 + 2 * A) {
+    out[N::obo + (tid - 64)] = accS[0];   // obo.. then ols.. are contiguous in the flat layout
+  }
+  if constexpr (MODE == MODE_GRAD) {
+    __syncthreads();
+    double v[1] = {s_loss};
+    block_reduce_store<1, false>(v, red_scratch, a.partial + (size_t)gridDim.x * P + (size_t)blockIdx.x * 3);
+  }
+}
+
+template <class N, int MODE>
+static int launch_tile(const UpdArgs& a, int* grid_out, cudaStream_t st) {
+  using SM = TileSmem<N, MODE>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B200RL_CUDA_CHECK(cudaFuncSetAttribute(update_tile_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)SM::bytes));
+    attr_done = true;
+  }
+  int per_sm = (int)((227 * 1024) / (SM::bytes + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 3) per_sm = 3;
+  long long grid = (long long)num_sms() * per_sm;
+  const long long ntiles = (a.B + T_TILE - 1) / T_TILE;
+  if (grid > ntiles) grid = ntiles;
+  if (grid > MAX_PARTIAL_BLOCKS) grid = MAX_PARTIAL_BLOCKS;
+  update_tile_kernel<N, MODE><<<(unsigned)grid, T_THREADS, SM::bytes, st>>>(a);
+  B200RL_LAUNCH_CHECK("update_tile_kernel");
+  *grid_out = (int)grid;
+  return 0;
+}
+
+int update_tile_launch(int mode, int obs_dim, int act_dim, const UpdArgs& a, int* grid_out, int* P_out, int* ols_out,
+                       cudaStream_t st) {
+  const int h1 = 32, h2 = 32;
+  B200RL_DISPATCH_NET_H(32, {
+    *P_out = NetT::P;
+    *ols_out = NetT::ols;
+    int rc = (mode == MODE_GRAD) ? launch_tile<NetT, MODE_GRAD>(a, grid_out, st)
+                                 : launch_tile<NetT, MODE_FVP>(a, grid_out, st);
+    if (rc) return rc;
+  });
+  return 0;
+}
+
+}  // namespace b200rl
