@@ -265,7 +265,7 @@ def main():
     kern["lfb_gram"] = dict(ms=timed(lambda: ops.lfb_gram(b, gram)), bytes=(4 * O + 2 + 4) * b.B, per_iter=1)
     kern["loss_kl"] = dict(ms=timed(lambda: ops.loss_kl(loss_kind, policy.theta32, dims, policy.min_std, b,
                                                         1.0 / b.B_global, out3)),
-                           bytes=samp_bytes * b.B, per_iter=2 if algo_name == "vpg" else 3)
+                           bytes=samp_bytes * b.B, per_iter=1 if algo_name == "vpg" else 2)
     kern["grad"] = dict(ms=timed(lambda: ops.grad(loss_kind, policy.theta32, dims, policy.min_std, b,
                                                   1.0 / b.B_global, g)), bytes=samp_bytes * b.B, per_iter=1)
     if algo_name == "trpo":

@@ -141,10 +141,12 @@ int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, 
                    const float* old_log_std, double scale, double* out, double* ws, void* stream);
 
 /* Flat gradient of the surrogate (theano.grad in conjugate_gradient_optimizer.py:184-186 /
- * first_order_optimizer.py:62-64): g_out [P] float64 = scale * sum over samples. */
+ * first_order_optimizer.py:62-64): g_out [P] float64 = scale * sum over samples.  loss_out (3 doubles or NULL)
+ * receives the b200rl_loss_kl triple of the same pass (loss, sum kl, max kl) at no extra cost. */
 int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std,
                 long long B, const float* obs, const float* act, const float* adv, const float* old_mean,
-                const float* old_log_std, double scale, double* g_out, double* ws, void* stream);
+                const float* old_log_std, double scale, double* g_out, double* loss_out, double* ws,
+                void* stream);
 
 /* Fisher/Hessian-vector product of mean KL at theta_old (PerlmutterHvp, conjugate_gradient_optimizer.py:22-55):
  * Hx_out [P] = scale * sum_samples J^T M J x  (+ reg_coeff*x and the log_std block added once: pass

@@ -551,7 +551,7 @@ int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, 
 
 int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std,
                 long long B, const float* obs, const float* act, const float* adv, const float* old_mean,
-                const float* old_log_std, double scale, double* g_out, double* ws, void* stream) {
+                const float* old_log_std, double scale, double* g_out, double* loss_out, double* ws, void* stream) {
   B200RL_REQUIRE(params_f32 && obs && act && adv && old_mean && old_log_std && g_out && ws && B > 0,
                  "grad: bad arguments");
   B200RL_REQUIRE(loss_kind == B200RL_LOSS_TRPO || loss_kind == B200RL_LOSS_VPG, "grad: bad loss kind");
@@ -593,7 +593,16 @@ int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int
   }
   mask_logstd_grad_kernel<<<1, 32, 0, st>>>(ols, act_dim, params_f32, a.log_min_std, g_out);
   B200RL_LAUNCH_CHECK("mask_logstd_grad_kernel");
-  (void)P;
+  if (loss_out != nullptr) {
+    // per-block (sum loss, sum kl, max kl) triples follow the first pass's [grid][P] partial vectors
+    const double* sc = ws + (size_t)grid * P;
+    double* tmp = ws + (size_t)grid * (P + 3) * 3 + P + 8;
+    int rc = launch_finalize_sum(sc, grid, 3, loss_out, scale, st);
+    if (rc) return rc;
+    rc = launch_finalize_max(sc, grid, 3, tmp, st);
+    if (rc) return rc;
+    B200RL_CUDA_CHECK(cudaMemcpyAsync(loss_out + 2, tmp + 2, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
 

@@ -47,16 +47,20 @@ __global__ void __launch_bounds__(T_THREADS) update_tile_kernel(UpdArgs a) {
   __syncthreads();
 
   // distribution constants
-  float ls_new[A], inv_std[A], ls_old[A], inv_std_old[A], Mmu[A];
+  float ls_new[A], inv_std[A], ls_old[A], inv_std_old[A], Mmu[A], var_new[A], var_new2[A], var_old[A];
   float sum_ls_new = 0.f, sum_ls_old = 0.f;
 #pragma unroll
   for (int k = 0; k < A; ++k) {
     ls_new[k] = clamp_log_std(sp[N::ols + k], a.log_min_std);
     const float sd = expf(ls_new[k]);
     inv_std[k] = 1.0f / sd;
-    Mmu[k] = 2.0f / (2.0f * sd * sd + 1e-8f);
+    var_new[k] = sd * sd;
+    var_new2[k] = 2.0f * sd * sd + 1e-8f;
+    Mmu[k] = 2.0f / var_new2[k];
     ls_old[k] = (MODE == MODE_FVP) ? ls_new[k] : a.old_log_std[k];
-    inv_std_old[k] = 1.0f / expf(ls_old[k]);
+    const float so = expf(ls_old[k]);
+    inv_std_old[k] = 1.0f / so;
+    var_old[k] = so * so;
     sum_ls_new += ls_new[k];
     sum_ls_old += ls_old[k];
   }
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(T_THREADS) update_tile_kernel(UpdArgs a) {
   double accS[NS];   // small-output accumulators of this thread's task (see below)
 #pragma unroll
   for (int k = 0; k < NS; ++k) accS[k] = 0.0;
-  double s_loss = 0.0;
+  double s_loss = 0.0, s_kl = 0.0, m_kl = -1.0e300;
 
   const long long ntiles = (a.B + T_TILE - 1) / T_TILE;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(T_THREADS) update_tile_kernel(UpdArgs a) {
           }
           mu[k] = s0 + s1;
         }
-        float z[A], zsq = 0.f, zsq_old = 0.f;
+        float z[A], zsq = 0.f, zsq_old = 0.f, kl = 0.f;
 #pragma unroll
         for (int k = 0; k < A; ++k) {
           const float act = a.act[(size_t)k * a.B + sl];
@@ -115,6 +119,8 @@ __global__ void __launch_bounds__(T_THREADS) update_tile_kernel(UpdArgs a) {
           zsq += z[k] * z[k];
           const float zo = (act - om) * inv_std_old[k];
           zsq_old += zo * zo;
+          const float dm = om - mu[k];
+          kl += (dm * dm + var_old[k] - var_new[k]) / var_new2[k] + ls_new[k] - ls_old[k];
         }
         const float adv_s = a.adv[sl];
         const float logp_new = -sum_ls_new - 0.5f * zsq - half_log2pi_A;
@@ -129,6 +135,7 @@ __global__ void __launch_bounds__(T_THREADS) update_tile_kernel(UpdArgs a) {
         }
         if (!valid) { w_s = 0.f; term = 0.f; }
         s_loss += (double)term;
+        if (valid) { s_kl += (double)kl; m_kl = fmax(m_kl, (double)kl); }
 #pragma unroll
         for (int k = 0; k < A; ++k) {
           dmu[k] = -w_s * z[k] * inv_std[k];
@@ -300,8 +307,11 @@ __global__ void __launch_bounds__(T_THREADS) update_tile_kernel(UpdArgs a) {
   }
   if constexpr (MODE == MODE_GRAD) {
     __syncthreads();
-    double v[1] = {s_loss};
-    block_reduce_store<1, false>(v, red_scratch, a.partial + (size_t)gridDim.x * P + (size_t)blockIdx.x * 3);
+    double v[2] = {s_loss, s_kl};
+    double mx[1] = {m_kl};
+    double* sc = a.partial + (size_t)gridDim.x * P + (size_t)blockIdx.x * 3;
+    block_reduce_store<2, false>(v, red_scratch, sc);
+    block_reduce_store<1, true>(mx, red_scratch, sc + 2);
   }
 }
 

@@ -139,12 +139,12 @@ def loss_kl(loss_kind, params32, dims, min_std, batch, scale, out):
            L.ptr(workspace(b.device)), _stream())
 
 
-def grad(loss_kind, params32, dims, min_std, batch, scale, g_out):
+def grad(loss_kind, params32, dims, min_std, batch, scale, g_out, loss_out=None):
     O, h1, h2, A = dims
     b = batch
     _chk(params32, F32, "params32"), _chk(g_out, F64, "g_out")
     L.call("b200rl_grad", loss_kind, L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
-           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), float(scale), L.ptr(g_out),
+           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), float(scale), L.ptr(g_out), L.ptr(loss_out),
            L.ptr(workspace(b.device)), _stream())
 
 

@@ -35,6 +35,7 @@ class ConjugateGradientOptimizer(object):
         self._comm = None
         self._bufs = None
         self._cache = None     # (policy version, batch id) -> (loss, mean_kl, max_kl)
+        self._g_key = None     # key for which the `g` buffer holds the flat gradient
         self.last_info = {}
 
     def update_opt(self, loss, target, leq_constraint, inputs=None, extra_inputs=None, constraint_name="constraint",
@@ -60,25 +61,33 @@ class ConjugateGradientOptimizer(object):
             self._comm.all_reduce_sum(out[:2])
             self._comm.all_reduce_max(out[2:])
 
-    def _eval(self, batch, sync=True):
-        """surrogate loss, mean KL, max KL at the target's current parameters (one pass over the batch)."""
+    def _eval(self, batch, want_grad=False):
+        """surrogate loss, mean KL, max KL at the target's current parameters (one pass over the batch).
+        want_grad: run the gradient pass instead, which yields the same triple for free and leaves the flat
+        gradient in the `g` buffer (f_loss + f_grad of cg_opt.py:248,253 fused into one pass)."""
         from .. import ops
         pol = self._target
         key = (pol.version, id(batch), batch.version)
         if self._cache is not None and self._cache[0] == key:
             return self._cache[1]
         b = self._buffers(pol.n_params, batch.device)
-        ops.loss_kl(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, b["out"])
+        if want_grad:
+            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, b["g"], b["out"])
+            if self._comm is not None and self._comm.active:
+                self._comm.all_reduce_sum(b["g"])
+            self._g_key = key
+        else:
+            ops.loss_kl(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, b["out"])
         self._allreduce_out3(b["out"])
         vals = tuple(float(v) for v in b["out"].cpu().numpy())
         self._cache = (key, vals)
         return vals
 
     def loss(self, inputs, extra_inputs=None):
-        return self._eval(_lane_batch(inputs))[0]
+        return self._eval(_lane_batch(inputs), want_grad=True)[0]
 
     def constraint_val(self, inputs, extra_inputs=None):
-        return self._eval(_lane_batch(inputs))[1]
+        return self._eval(_lane_batch(inputs), want_grad=True)[1]
 
     def optimize(self, inputs, extra_inputs=None, subsample_grouped_inputs=None):
         from .. import ops
@@ -92,11 +101,12 @@ class ConjugateGradientOptimizer(object):
         ar = (lambda t: comm.all_reduce_sum(t)) if world > 1 else (lambda t: t)
 
         logger.log("computing loss before")
-        loss_before = self._eval(batch)[0]
+        loss_before = self._eval(batch, want_grad=True)[0]
         logger.log("performing update")
         logger.log("computing descent direction")
-        ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, scale, b["g"])
-        ar(b["g"])
+        if self._g_key != (pol.version, id(batch), batch.version):
+            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, scale, b["g"])
+            ar(b["g"])
 
         def Hx(vec, out):
             ops.fvp(pol.theta32, pol.dims, pol.min_std, batch, vec, scale, self._reg_coeff, 1.0 / world, out)

@@ -24,6 +24,7 @@ class FirstOrderOptimizer(object):
         self._m = self._v = self._g = self._out = None
         self._t = 0
         self._cache = None
+        self._g_key = None
 
     def update_opt(self, loss, target, inputs=None, extra_inputs=None, gradients=None, comm=None, **kwargs):
         self._loss_kind = loss
@@ -39,14 +40,23 @@ class FirstOrderOptimizer(object):
             z = lambda n=P: torch.zeros(n, dtype=torch.float64, device=dev)
             self._m, self._v, self._g, self._out = z(), z(), z(), z(3)
 
-    def _eval(self, batch):
+    def _eval(self, batch, want_grad=False):
+        """(loss, mean_kl, max_kl); want_grad runs the gradient pass, which yields the triple for free and leaves the
+        flat gradient in self._g (f_loss + the gradient half of f_opt fused)."""
         from .. import ops
         pol = self._target
         key = (pol.version, id(batch), batch.version)
         if self._cache is not None and self._cache[0] == key:
             return self._cache[1]
         self._state(batch.device)
-        ops.loss_kl(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, self._out)
+        if want_grad:
+            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, self._g,
+                     self._out)
+            if self._comm is not None and self._comm.active:
+                self._comm.all_reduce_sum(self._g)
+            self._g_key = key
+        else:
+            ops.loss_kl(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, self._out)
         if self._comm is not None and self._comm.active:
             self._comm.all_reduce_sum(self._out[:2])
             self._comm.all_reduce_max(self._out[2:])
@@ -55,7 +65,7 @@ class FirstOrderOptimizer(object):
         return vals
 
     def loss(self, inputs, extra_inputs=None):
-        return self._eval(_lane_batch(inputs))[0]
+        return self._eval(_lane_batch(inputs), want_grad=True)[0]
 
     def kl_stats(self, inputs):
         """(mean_kl, max_kl): the f_kl of rllab/algos/vpg.py:100-103, same pass as the loss."""
@@ -69,11 +79,12 @@ class FirstOrderOptimizer(object):
             raise NotImplementedError("mini-batch epochs are not on the B200 hot path (VPG uses batch_size=None)")
         pol = self._target
         self._state(batch.device)
-        last_loss = self._eval(batch)[0]
+        last_loss = self._eval(batch, want_grad=True)[0]
         for epoch in range(self._max_epochs):
-            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, self._g)
-            if self._comm is not None and self._comm.active:
-                self._comm.all_reduce_sum(self._g)
+            if self._g_key != (pol.version, id(batch), batch.version):
+                ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, self._g)
+                if self._comm is not None and self._comm.active:
+                    self._comm.all_reduce_sum(self._g)
             self._t += 1
             ops.adam_step(pol.theta64, pol.theta32, self._g, self._m, self._v, self._t, self._learning_rate, self._b1,
                           self._b2, self._eps)
