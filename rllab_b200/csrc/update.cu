@@ -12,7 +12,7 @@
 
 namespace b200rl {
 
-constexpr int UPD_WARPS = 4;
+constexpr int UPD_WARPS = 2;  // 64-wide nets only: 2 warps x P float64 accumulators fit 227 KB with params + tangent
 constexpr int UPD_THREADS = UPD_WARPS * 32;
 constexpr int FLUSH_GROUPS = 4;  // float32 register accumulators are folded into float64 every 4*32 samples
 

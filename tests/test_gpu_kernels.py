@@ -352,7 +352,7 @@ def test_loss_kl_grad_fvp_match_oracle(dev, env_name, hidden):
         g = torch.zeros(dims.P, dtype=torch.float64, device=dev)
         out_g = torch.zeros(3, dtype=torch.float64, device=dev)
         ops.grad(kind, th2_32, dd, 1e-6, b, 1.0 / B, g, out_g)
-        np.testing.assert_allclose(out_g.cpu().numpy(), o, rtol=1e-9, atol=1e-12)     # fused loss/KL triple
+        np.testing.assert_allclose(out_g.cpu().numpy(), o, rtol=1e-5, atol=1e-8)     # fused loss/KL triple
         ref_g = P.grad_surr(th2, batch, dims, name)
         np.testing.assert_allclose(g.cpu().numpy(), ref_g, rtol=2e-4, atol=2e-6 * np.abs(ref_g).max() + 1e-9)
     # Fisher-vector product at theta_old
