@@ -28,7 +28,9 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 
 // Dense layer, thread-per-sample, weights W [NIN][NOUT] row-major + bias in shared memory (broadcast LDS.128).
 // Output pairs (j, j+1) share one packed FFMA2; even and odd inputs accumulate in separate chains (canonical order).
-template <int NIN, int NOUT, bool BIAS = true>
+// FENCE > 0 inserts a compiler memory barrier every FENCE input rows: it bounds how many weight loads ptxas may hoist
+// ahead (each LDS.128 holds 4 registers), which keeps the big fused kernels from spilling.
+template <int NIN, int NOUT, bool BIAS = true, int FENCE = 0>
 __device__ __forceinline__ void dense_thread(const float* __restrict__ W, const float* __restrict__ b,
                                              const float (&in)[NIN], float (&pre)[NOUT]) {
   float2 ae[NOUT / 2], ao[NOUT / 2];
@@ -42,6 +44,7 @@ __device__ __forceinline__ void dense_thread(const float* __restrict__ W, const 
   }
 #pragma unroll
   for (int i = 0; i < NIN; ++i) {
+    if (FENCE > 0 && i > 0 && (i % FENCE) == 0) asm volatile("" ::: "memory");
     const float2 xin = make_float2(in[i], in[i]);
 #pragma unroll
     for (int j = 0; j < NOUT; j += 4) {

@@ -9,7 +9,7 @@
 //
 // Replaces f_grad / f_Hx_plain of rllab/optimizers/conjugate_gradient_optimizer.py:184-215,22-55 and the gradient
 // half of f_opt in rllab/optimizers/first_order_optimizer.py:62-76.
-#include "update_common.cuh"
+#include "tile_phase_a.cuh"
 
 namespace b200rl {
 
@@ -30,7 +30,7 @@ struct TileSmem {
 };
 
 template <class N, int MODE>
-__global__ void __launch_bounds__(T_THREADS) update_tile_kernel(UpdArgs a) {
+__global__ void __launch_bounds__(T_THREADS, 2) update_tile_kernel(UpdArgs a) {
   using SM = TileSmem<N, MODE>;
   constexpr int O = N::O, H = 32, A = N::A, P = N::P, LD = T_LD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -47,24 +47,24 @@ __global__ void __launch_bounds__(T_THREADS) update_tile_kernel(UpdArgs a) {
   __syncthreads();
 
   // distribution constants
-  float ls_new[A], inv_std[A], ls_old[A], inv_std_old[A], Mmu[A], var_new[A], var_new2[A], var_old[A];
-  float sum_ls_new = 0.f, sum_ls_old = 0.f;
+  TileDist D;
+  D.sum_ls_new = 0.f; D.sum_ls_old = 0.f;
 #pragma unroll
   for (int k = 0; k < A; ++k) {
-    ls_new[k] = clamp_log_std(sp[N::ols + k], a.log_min_std);
-    const float sd = expf(ls_new[k]);
-    inv_std[k] = 1.0f / sd;
-    var_new[k] = sd * sd;
-    var_new2[k] = 2.0f * sd * sd + 1e-8f;
-    Mmu[k] = 2.0f / var_new2[k];
-    ls_old[k] = (MODE == MODE_FVP) ? ls_new[k] : a.old_log_std[k];
-    const float so = expf(ls_old[k]);
-    inv_std_old[k] = 1.0f / so;
-    var_old[k] = so * so;
-    sum_ls_new += ls_new[k];
-    sum_ls_old += ls_old[k];
+    D.ls_new[k] = clamp_log_std(sp[N::ols + k], a.log_min_std);
+    const float sd = expf(D.ls_new[k]);
+    D.inv_std[k] = 1.0f / sd;
+    D.var_new[k] = sd * sd;
+    D.var_new2[k] = 2.0f * sd * sd + 1e-8f;
+    D.Mmu[k] = 2.0f / D.var_new2[k];
+    D.ls_old[k] = (MODE == MODE_FVP) ? D.ls_new[k] : a.old_log_std[k];
+    const float so = expf(D.ls_old[k]);
+    D.inv_std_old[k] = 1.0f / so;
+    D.var_old[k] = so * so;
+    D.sum_ls_new += D.ls_new[k];
+    D.sum_ls_old += D.ls_old[k];
   }
-  const float half_log2pi_A = 0.5f * (float)A * 1.8378770664093453f;
+  D.half_log2pi_A = 0.5f * (float)A * 1.8378770664093453f;
 
   // ---- Gram ownership
   const int w1_tile = tid & 63, kh = tid >> 6;
@@ -86,113 +86,7 @@ __global__ void __launch_bounds__(T_THREADS) update_tile_kernel(UpdArgs a) {
     const long long s = tile * T_TILE + tid;
     const bool valid = s < a.B;
     // ================= phase A: per-sample forward / (tangent) / backward, staged to shared memory
-    {
-      float x[O], h1[H], h2[H], d2[H], dmu[A];
-      const long long sl = valid ? s : a.B - 1;
-#pragma unroll
-      for (int o = 0; o < O; ++o) x[o] = a.obs[(size_t)o * a.B + sl];
-      dense_thread<O, H>(sp + N::oW0, sp + N::ob0, x, h1);
-#pragma unroll
-      for (int j = 0; j < H; ++j) h1[j] = tanh_f(h1[j]);
-      dense_thread<H, H>(sp + N::oW1, sp + N::ob1, h1, h2);
-      asm volatile("" ::: "memory");   // do not keep shared-memory weights live in registers across sections
-#pragma unroll
-      for (int j = 0; j < H; ++j) h2[j] = tanh_f(h2[j]);
-      if constexpr (MODE == MODE_GRAD) {
-        float mu[A];
-#pragma unroll
-        for (int k = 0; k < A; ++k) {
-          float s0 = sp[N::obo + k], s1 = 0.f;
-#pragma unroll
-          for (int j = 0; j < H; j += 2) {
-            s0 = fmaf(h2[j], sp[N::oWo + j * A + k], s0);
-            s1 = fmaf(h2[j + 1], sp[N::oWo + (j + 1) * A + k], s1);
-          }
-          mu[k] = s0 + s1;
-        }
-        float z[A], zsq = 0.f, zsq_old = 0.f, kl = 0.f;
-#pragma unroll
-        for (int k = 0; k < A; ++k) {
-          const float act = a.act[(size_t)k * a.B + sl];
-          const float om = a.old_mean[(size_t)k * a.B + sl];
-          z[k] = (act - mu[k]) * inv_std[k];
-          zsq += z[k] * z[k];
-          const float zo = (act - om) * inv_std_old[k];
-          zsq_old += zo * zo;
-          const float dm = om - mu[k];
-          kl += (dm * dm + var_old[k] - var_new[k]) / var_new2[k] + ls_new[k] - ls_old[k];
-        }
-        const float adv_s = a.adv[sl];
-        const float logp_new = -sum_ls_new - 0.5f * zsq - half_log2pi_A;
-        float w_s, term;
-        if (a.loss_kind == B200RL_LOSS_TRPO) {
-          const float logp_old = -sum_ls_old - 0.5f * zsq_old - half_log2pi_A;
-          w_s = expf(logp_new - logp_old) * adv_s;
-          term = -w_s;
-        } else {
-          w_s = adv_s;
-          term = -logp_new * adv_s;
-        }
-        if (!valid) { w_s = 0.f; term = 0.f; }
-        s_loss += (double)term;
-        if (valid) { s_kl += (double)kl; m_kl = fmax(m_kl, (double)kl); }
-#pragma unroll
-        for (int k = 0; k < A; ++k) {
-          dmu[k] = -w_s * z[k] * inv_std[k];
-          stage[(SM::rDM + k) * LD + tid] = dmu[k];
-          stage[(SM::rDL + k) * LD + tid] = -w_s * (z[k] * z[k] - 1.0f);
-        }
-      } else {
-        // tangent forward J x (x = sv): t1 = (1-h1^2)(x V0 + vb0); t2 = (1-h2^2)(t1 W1 + h1 V1 + vb1)
-        float t1[H], t2[H], p2b[H];
-        asm volatile("" ::: "memory");   // do not keep shared-memory weights live in registers across sections
-        dense_thread<O, H>(sv + N::oW0, sv + N::ob0, x, t1);
-#pragma unroll
-        for (int j = 0; j < H; ++j) t1[j] *= (1.0f - h1[j] * h1[j]);
-        dense_thread<H, H>(sp + N::oW1, sv + N::ob1, t1, t2);
-        asm volatile("" ::: "memory");   // do not keep shared-memory weights live in registers across sections
-        dense_thread<H, H, false>(sv + N::oW1, nullptr, h1, p2b);
-#pragma unroll
-        for (int j = 0; j < H; ++j) t2[j] = (t2[j] + p2b[j]) * (1.0f - h2[j] * h2[j]);
-#pragma unroll
-        for (int k = 0; k < A; ++k) {
-          float s0 = sv[N::obo + k], s1 = 0.f;
-#pragma unroll
-          for (int j = 0; j < H; ++j) {
-            s0 = fmaf(t2[j], sp[N::oWo + j * A + k], s0);
-            s1 = fmaf(h2[j], sv[N::oWo + j * A + k], s1);
-          }
-          dmu[k] = valid ? (s0 + s1) * Mmu[k] : 0.f;
-          stage[(SM::rDM + k) * LD + tid] = dmu[k];
-          stage[(SM::rDL + k) * LD + tid] = 0.f;
-        }
-      }
-      asm volatile("" ::: "memory");   // do not keep shared-memory weights live in registers across sections
-      // backward: d2 = (dmu Wout^T) (1-h2^2); d1 = (d2 W1^T) (1-h1^2)
-#pragma unroll
-      for (int j = 0; j < H; ++j) {
-        float sacc = 0.f;
-#pragma unroll
-        for (int k = 0; k < A; ++k) sacc = fmaf(dmu[k], sp[N::oWo + j * A + k], sacc);
-        d2[j] = sacc * (1.0f - h2[j] * h2[j]);
-        stage[(SM::rH2 + j) * LD + tid] = h2[j];
-        stage[(SM::rD2 + j) * LD + tid] = d2[j];
-      }
-#pragma unroll
-      for (int i = 0; i < H; ++i) {
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < H; j += 4) {
-          const float4 w = *reinterpret_cast<const float4*>(sp + N::oW1 + i * H + j);
-          acc = ffma2(make_float2(d2[j], d2[j + 1]), make_float2(w.x, w.y), acc);
-          acc = ffma2(make_float2(d2[j + 2], d2[j + 3]), make_float2(w.z, w.w), acc);
-        }
-        stage[(SM::rH1 + i) * LD + tid] = h1[i];
-        stage[(SM::rD1 + i) * LD + tid] = (acc.x + acc.y) * (1.0f - h1[i] * h1[i]);
-      }
-#pragma unroll
-      for (int o = 0; o < O; ++o) stage[(SM::rX + o) * LD + tid] = x[o];
-    }
+    tile_phase_a<N, MODE, SM, LD>(a, sp, sv, stage, D, valid ? s : a.B - 1, valid, tid, s_loss, s_kl, m_kl);
     __syncthreads();
     // ================= phase B: Gram accumulation over the tile
     {
