@@ -8,6 +8,8 @@
 // f_loss_constraint), :22-55 (PerlmutterHvp f_Hx_plain), rllab/optimizers/first_order_optimizer.py:62-76 (grad part
 // of f_opt), rllab/algos/vpg.py:100-103 (f_kl), over rllab/algos/npo.py:72-82 / vpg.py:88-99 and
 // rllab/distributions/diagonal_gaussian.py:14-34,58-69.
+#include <stdlib.h>
+
 #include "update_common.cuh"
 
 namespace b200rl {
@@ -495,6 +497,15 @@ static int launch_update(const UpdArgs& a0, int grid, cudaStream_t st) {
   return 0;
 }
 
+int update_impl() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("B200RL_UPDATE_IMPL");
+    cached = (e == nullptr || !strcmp(e, "gemm")) ? 0 : (!strcmp(e, "tile") ? 1 : 2);
+  }
+  return cached;
+}
+
 template <class N, int MODE>
 static int update_grid(long long B) {
   using SM = UpdSmem<N, MODE>;
@@ -561,8 +572,10 @@ int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int
   a.obs = obs; a.act = act; a.adv = adv; a.old_mean = old_mean; a.old_log_std = old_log_std;
   a.loss_kind = loss_kind; a.partial = ws;
   int grid = 0, P = 0, ols = 0;
-  if (h1 == 32 && h2 == 32) {
-    int rc = update_tile_launch(MODE_GRAD, obs_dim, act_dim, a, &grid, &P, &ols, st);
+  const int impl = update_impl();
+  if (h1 == h2 && (impl == 0 || (impl == 1 && h1 == 32))) {
+    int rc = (impl == 0) ? update_gemm_launch(MODE_GRAD, obs_dim, h1, act_dim, a, &grid, &P, &ols, st)
+                         : update_tile_launch(MODE_GRAD, obs_dim, act_dim, a, &grid, &P, &ols, st);
     if (rc) return rc;
     rc = launch_finalize_sum(ws, grid, P, g_out, scale, st);
     if (rc) return rc;
@@ -615,8 +628,10 @@ int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim
   a.params = params_f32; a.xvec = x; a.log_min_std = min_std > 0.f ? logf(min_std) : -INFINITY; a.B = B;
   a.obs = obs; a.partial = ws;
   int grid = 0, P = 0, ols = 0;
-  if (h1 == 32 && h2 == 32) {
-    int rc = update_tile_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st);
+  const int impl = update_impl();
+  if (h1 == h2 && (impl == 0 || (impl == 1 && h1 == 32))) {
+    int rc = (impl == 0) ? update_gemm_launch(MODE_FVP, obs_dim, h1, act_dim, a, &grid, &P, &ols, st)
+                         : update_tile_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st);
     if (rc) return rc;
     rc = launch_finalize_sum(ws, grid, P, Hx_out, scale, st);
     if (rc) return rc;

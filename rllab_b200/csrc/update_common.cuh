@@ -23,4 +23,11 @@ struct UpdArgs {
 int update_tile_launch(int mode, int obs_dim, int act_dim, const UpdArgs& a, int* grid_out, int* P_out, int* ols_out,
                        cudaStream_t st);
 
+// 32- and 64-wide nets: the tiled-GEMM formulation (update_gemm.cu); same contract as update_tile_launch.
+int update_gemm_launch(int mode, int obs_dim, int h, int act_dim, const UpdArgs& a, int* grid_out, int* P_out,
+                       int* ols_out, cudaStream_t st);
+
+// which implementation b200rl_grad / b200rl_fvp use: env B200RL_UPDATE_IMPL = gemm (default) | tile | warp
+int update_impl();
+
 }  // namespace b200rl
