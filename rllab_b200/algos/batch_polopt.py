@@ -34,6 +34,7 @@ class BatchPolopt(RLAlgorithm):
             sampler_cls = LaneSampler
         if sampler_args is None:
             sampler_args = dict()
+        self._sampler_cls, self._sampler_args = sampler_cls, dict(sampler_args)
         self.sampler = sampler_cls(self, **sampler_args)
 
     def start_worker(self):
@@ -89,7 +90,16 @@ class BatchPolopt(RLAlgorithm):
     def optimize_policy(self, itr, samples_data):
         raise NotImplementedError
 
+    # snapshots pickle `algo` (batch_polopt.py:126, logger.py:216-232); resuming = unpickle + train()
+    # (scripts/run_experiment_lite.py:111-115): device buffers are dropped and the sampler is rebuilt.
     def __getstate__(self):
         d = dict(self.__dict__)
         d["sampler"] = None
+        args = dict(d["_sampler_args"])
+        args.pop("comm", None)
+        d["_sampler_args"] = args
         return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self.sampler = self._sampler_cls(self, **self._sampler_args)

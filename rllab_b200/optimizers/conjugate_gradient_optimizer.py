@@ -38,6 +38,9 @@ class ConjugateGradientOptimizer(object):
         self._g_key = None     # key for which the `g` buffer holds the flat gradient
         self.last_info = {}
 
+    def __getstate__(self):
+        return _drop_device_state(self.__dict__, ("_bufs", "_cache", "_g_key", "_comm"))
+
     def update_opt(self, loss, target, leq_constraint, inputs=None, extra_inputs=None, constraint_name="constraint",
                    comm=None, *args, **kwargs):
         constraint_term, constraint_value = leq_constraint
@@ -149,6 +152,13 @@ class ConjugateGradientOptimizer(object):
         logger.log("optimization finished")
         self.last_info = dict(loss_before=loss_before, loss=loss, constraint_val=constraint_val, n_iter=n_iter,
                               rejected=rejected)
+
+
+def _drop_device_state(obj_dict, keys):
+    d = dict(obj_dict)
+    for k in keys:
+        d[k] = None
+    return d
 
 
 def _lane_batch(inputs):

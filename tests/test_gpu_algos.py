@@ -233,3 +233,39 @@ def test_policy_api_and_pickle(dev):
     pol2 = pickle.loads(pickle.dumps(pol))
     np.testing.assert_array_equal(pol2.get_param_values(), flat * 0.5)
     assert pol.distribution.entropy(dict(log_std=np.zeros((1, 1))))[0] == pytest.approx(1.41894, abs=1e-5)
+
+
+@pytest.mark.parametrize("algo_name", ["trpo", "vpg"])
+def test_snapshot_and_resume(dev, algo_name, tmp_path):
+    """logger.save_itr_params + resume_from semantics (misc/logger.py:216-232, scripts/run_experiment_lite.py:111-115):
+    a resumed run continues at current_itr with identical parameters (and Adam state) and produces the same next
+    iterate as the uninterrupted run."""
+    from rllab_b200.misc import logger
+    logger.set_snapshot_dir(str(tmp_path))
+    logger.set_snapshot_mode("last")
+    try:
+        algo = _algo("cartpole", algo_name, 256, 50, n_itr=2)
+        algo.train()
+        theta2 = algo.policy.get_param_values()
+        data = pickle.load(open(str(tmp_path / "params.pkl"), "rb"))
+    finally:
+        logger.set_snapshot_mode("none")
+        logger.set_snapshot_dir(None)
+    assert data["itr"] == 1 and set(data) >= {"itr", "policy", "baseline", "env", "algo"}
+    np.testing.assert_array_equal(data["policy"].get_param_values(), theta2)
+    resumed = data["algo"]
+    assert resumed.current_itr == 2
+    resumed.n_itr = 3
+    resumed.train()                      # runs exactly iteration 2
+    # same three iterations in one process; train() re-runs init_opt on resume, which -- exactly like the reference,
+    # where lasagne's Adam state lives in shared variables created by update_opt -- resets the optimizer state
+    algo3 = _algo("cartpole", algo_name, 256, 50, n_itr=3)
+    algo3.start_worker()
+    algo3.init_opt()
+    algo3.train_itr(0)
+    algo3.train_itr(1)
+    algo3.init_opt()
+    algo3.train_itr(2)
+    rel = np.max(np.abs(resumed.policy.get_param_values() - algo3.policy.get_param_values())) / \
+        np.max(np.abs(algo3.policy.get_param_values()))
+    assert rel < 1e-12, rel

@@ -1,0 +1,109 @@
+"""CPU: host-side pieces of the plugin API that need no GPU (reference known answers where they exist)."""
+import pickle
+
+import numpy as np
+import pytest
+
+
+def test_truncate_paths_reference_known_answer(golden):
+    """tests/test_sampler.py:4-32 of the reference, plus the golden lengths produced by the reference itself."""
+    from rllab_b200.sampler.parallel_sampler import truncate_paths
+    mk = lambda l: dict(observations=np.zeros((l, 1)), actions=np.zeros((l, 1)), rewards=np.zeros(l), env_infos=dict(),
+                        agent_infos=dict(lala=np.zeros(l)))
+    paths = [mk(100), mk(50)]
+    truncated = truncate_paths(paths, 130)
+    assert len(truncated) == 2 and len(truncated[-1]["observations"]) == 30 and len(truncated[0]["observations"]) == 100
+    assert len(paths) == 2 and len(paths[-1]["observations"]) == 50          # input not modified
+    assert len(truncated[-1]["agent_infos"]["lala"]) == 30
+    for ms in (130, 150, 1, 249, 250, 400):
+        got = [len(p["rewards"]) for p in truncate_paths([mk(int(l)) for l in golden["tr_lens"]], ms)]
+        assert got == list(golden["tr_%d" % ms])
+
+
+def test_box_space_reference_semantics():
+    """tests/test_spaces.py:20-27 (Box flatten / unflatten round trips)."""
+    from rllab_b200.spaces import Box
+    b = Box(-1.0, 1.0, (3, 4))
+    x = b.sample()
+    assert b.contains(x) and b.flat_dim == 12 and b.shape == (3, 4)
+    np.testing.assert_array_equal(b.unflatten(b.flatten(x)), x)
+    xs = np.stack([b.sample() for _ in range(5)])
+    np.testing.assert_array_equal(b.unflatten_n(b.flatten_n(xs)), xs)
+    assert Box(np.array([-1., -2.]), np.array([2., 4.])) == Box(np.array([-1., -2.]), np.array([2., 4.]))
+    assert not b.contains(np.full((3, 4), 2.0))
+
+
+def test_linear_feature_baseline_host_api_matches_reference_golden(golden):
+    """fit(paths)/predict(path) on host path dicts == the reference's own LinearFeatureBaseline (golden ps_*_fit)."""
+    from oracle import sampler as S
+    from rllab_b200.baselines.linear_feature_baseline import LinearFeatureBaseline
+    traj = {k[len("ps_in_"):]: v for k, v in golden.items() if k.startswith("ps_in_") and k != "ps_in_coeffs_prev"}
+    paths = S.lanes_to_paths(traj)
+    out = S.process_samples_lanes(traj, None, 0.99, 1.0)
+    for p in paths:
+        L = len(p["rewards"])
+        p["returns"] = out["ret"][p["_t0"]:p["_t0"] + L, p["_lane"]]
+    bl = LinearFeatureBaseline()
+    assert np.array_equal(bl.predict(paths[0]), np.zeros(len(paths[0]["rewards"])))     # :41-42
+    bl.fit(paths)
+    pred = np.concatenate([bl.predict(p) for p in paths])
+    bl_ref = LinearFeatureBaseline()
+    bl_ref.set_param_values(golden["ps_a_fit"])
+    np.testing.assert_allclose(pred, np.concatenate([bl_ref.predict(p) for p in paths]), rtol=1e-6, atol=1e-8)
+    bl2 = pickle.loads(pickle.dumps(bl))
+    np.testing.assert_array_equal(bl2.get_param_values(), bl.get_param_values())
+
+
+def test_diagonal_gaussian_host_api_matches_reference_golden(golden):
+    from rllab_b200.distributions.diagonal_gaussian import DiagonalGaussian
+    g = golden
+    d = DiagonalGaussian(2)
+    np.testing.assert_allclose(d.kl(dict(mean=g["dg_om"], log_std=g["dg_ol"]), dict(mean=g["dg_nm"], log_std=g["dg_nl"])),
+                               g["dg_kl"], rtol=1e-13)
+    np.testing.assert_allclose(d.log_likelihood(g["dg_xs"], dict(mean=g["dg_nm"], log_std=g["dg_nl"])), g["dg_ll"], rtol=1e-13)
+    np.testing.assert_allclose(d.entropy(dict(log_std=g["dg_nl"])), g["dg_ent"], rtol=1e-13)
+    assert d.dist_info_keys == ["mean", "log_std"] and d.dim == 2
+
+
+def test_policy_construction_and_errors_without_gpu():
+    from rllab_b200 import _lib
+    from rllab_b200.envs.box2d.cartpole_env import CartpoleEnv
+    from rllab_b200.envs.normalized_env import normalize
+    from rllab_b200.policies.gaussian_mlp_policy import GaussianMLPPolicy
+    env = normalize(CartpoleEnv())
+    assert env.action_space.bounds[0][0] == -1.0 and env.observation_space.flat_dim == 4
+    pol = GaussianMLPPolicy(env.spec, hidden_sizes=(32, 32), seed=4)
+    flat = pol.get_param_values()
+    assert flat.shape == (1250,) and np.all(flat[-1:] == 0.0)                    # log(init_std=1)
+    W0 = pol.flat_to_params(flat)[0]
+    assert W0.shape == (4, 32) and np.abs(W0).max() <= np.sqrt(6.0 / 36) + 1e-12   # GlorotUniform bound
+    pol.set_param_values(flat * 2)
+    np.testing.assert_array_equal(pol.get_param_values(), flat * 2)
+    pol2 = pickle.loads(pickle.dumps(pol))
+    np.testing.assert_array_equal(pol2.get_param_values(), flat * 2)
+    with pytest.raises(NotImplementedError):
+        GaussianMLPPolicy(env.spec, adaptive_std=True)
+    with pytest.raises(_lib.B200RLError):
+        GaussianMLPPolicy(env.spec, hidden_sizes=(16, 16))
+    with pytest.raises(NotImplementedError):
+        normalize(CartpoleEnv(), normalize_obs=True)
+    from rllab_b200.optimizers.conjugate_gradient_optimizer import ConjugateGradientOptimizer
+    with pytest.raises(NotImplementedError):
+        ConjugateGradientOptimizer(subsample_factor=0.5)
+
+
+def test_logger_tabular_and_snapshot(tmp_path):
+    from rllab_b200.misc import logger
+    logger.set_quiet(True)
+    logger.set_snapshot_dir(str(tmp_path))
+    logger.set_snapshot_mode("last")
+    with logger.prefix("itr #0 | "):
+        logger.record_tabular("AverageReturn", 1.5)
+        logger.record_tabular("NumTrajs", 7)
+        logger.dump_tabular()
+    assert logger.get_last_table() == {"AverageReturn": 1.5, "NumTrajs": 7}
+    logger.save_itr_params(0, dict(itr=0, x=np.arange(3)))
+    d = pickle.load(open(str(tmp_path / "params.pkl"), "rb"))
+    assert d["itr"] == 0
+    logger.set_snapshot_mode("none")
+    logger.set_snapshot_dir(None)
