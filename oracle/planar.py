@@ -354,11 +354,12 @@ class SwimmerEnv(LaneEnv):
 
 
 class HopperEnv(LaneEnv):
-    """rllab/envs/mujoco/hopper_env.py:19-61.  state = [qpos(6), qvel(6), ctrl(3)];
+    """rllab/envs/mujoco/hopper_env.py:19-61.  state = [qpos(6), qvel(6), ctrl(3), qfrc_constraint(6), comX, comY]
+    (the last 8 cache mj_forward's outputs at the current state, as the CUDA env does; obs recomputes them here);
     obs = [q0, q2..q5, clip(qvel,+-10), clip(qfrc_constraint,+-10), com(3)];
     reward = comvel_x + 1 - 0.5*0.01*sum((a/200)^2); done = not(finite and |state[3:]|<100 and z>.7 and |pitch|<.2)."""
     name, kind = "hopper", 4
-    O, A, S, K = 20, 3, 15, 12
+    O, A, S, K = 20, 3, 23, 12
     noise_kind = "normal"
     lb, ub = (-200.0,) * 3, (200.0,) * 3
 
@@ -371,7 +372,13 @@ class HopperEnv(LaneEnv):
         raw = np.asarray(raw, dt)
         q = np.asarray(self.m.q0, dt).reshape(-1, 1) + dt(0.01) * raw[:6]
         v = dt(0.1) * raw[6:12]
-        return np.concatenate([q, v, np.zeros((3, raw.shape[1]), dt)]).astype(dt)
+        s = np.concatenate([q, v, np.zeros((3, raw.shape[1]), dt)]).astype(dt)
+        return self._with_cache(s)
+
+    def _with_cache(self, s15):
+        dt = self.dtype
+        _, qfc, kin = dynamics(self.m, list(s15[:6]), list(s15[6:12]), s15[12:15], dt)
+        return np.concatenate([s15[:15], np.stack(qfc), np.stack([kin["comX"], kin["comY"]])]).astype(dt)
 
     def obs(self, s):
         dt = self.dtype
@@ -389,7 +396,7 @@ class HopperEnv(LaneEnv):
         st = np.concatenate([q, v])
         notdone = np.isfinite(st).all(axis=0) & (np.abs(st[3:]) < 100).all(axis=0) & (st[0] > 0.7) & \
             (np.abs(st[2]) < 0.2)
-        s2 = np.concatenate([q, v, np.asarray(u, dt)]).astype(dt)
+        s2 = self._with_cache(np.concatenate([q, v, np.asarray(u, dt)]).astype(dt))
         return s2, r.astype(dt), ~notdone
 
 

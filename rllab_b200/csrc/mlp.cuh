@@ -65,14 +65,58 @@ __device__ __forceinline__ void dense_thread(const float* __restrict__ W, const 
   }
 }
 
+// Same layer with the INPUT vector read from this thread's column of a shared-memory matrix (in_col[i * ld]) and a
+// rolled loop over input pairs: for 64-wide layers the fully unrolled form is ~90 KB of code per layer and thrashes
+// the instruction cache (ncu: "no_instructions" was the top stall of the Hopper rollout, icc hit rate 73 %).
+template <int NIN, int NOUT>
+__device__ __forceinline__ void dense_thread_col(const float* __restrict__ W, const float* __restrict__ b,
+                                                 const float* in_col, int ld, float (&pre)[NOUT]) {
+  static_assert(NIN % 2 == 0, "even number of inputs");
+  float2 ae[NOUT / 2], ao[NOUT / 2];
+#pragma unroll
+  for (int j = 0; j < NOUT; j += 4) {
+    const float4 bb = *reinterpret_cast<const float4*>(b + j);
+    ae[j / 2] = make_float2(bb.x, bb.y);
+    ae[j / 2 + 1] = make_float2(bb.z, bb.w);
+    ao[j / 2] = make_float2(0.f, 0.f);
+    ao[j / 2 + 1] = make_float2(0.f, 0.f);
+  }
+#pragma unroll 1
+  for (int i = 0; i < NIN; i += 2) {
+    const float a0 = in_col[i * ld], a1 = in_col[(i + 1) * ld];
+    const float2 x0 = make_float2(a0, a0), x1 = make_float2(a1, a1);
+#pragma unroll
+    for (int j = 0; j < NOUT; j += 4) {
+      const float4 w0 = *reinterpret_cast<const float4*>(W + i * NOUT + j);
+      const float4 w1 = *reinterpret_cast<const float4*>(W + (i + 1) * NOUT + j);
+      ae[j / 2] = ffma2(x0, make_float2(w0.x, w0.y), ae[j / 2]);
+      ae[j / 2 + 1] = ffma2(x0, make_float2(w0.z, w0.w), ae[j / 2 + 1]);
+      ao[j / 2] = ffma2(x1, make_float2(w1.x, w1.y), ao[j / 2]);
+      ao[j / 2 + 1] = ffma2(x1, make_float2(w1.z, w1.w), ao[j / 2 + 1]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NOUT; j += 2) {
+    pre[j] = ae[j / 2].x + ao[j / 2].x;
+    pre[j + 1] = ae[j / 2].y + ao[j / 2].y;
+  }
+}
+
 // Thread-per-sample forward, parameters in shared memory.
 template <class N>
 __device__ __forceinline__ void mlp_forward_thread(const float* __restrict__ sp, const float (&x)[N::O],
-                                                   float (&h1)[N::H1], float (&h2)[N::H2], float (&mu)[N::A]) {
+                                                   float (&h1)[N::H1], float (&h2)[N::H2], float (&mu)[N::A],
+                                                   float* hcol = nullptr, int hld = 0) {
   dense_thread<N::O, N::H1>(sp + N::oW0, sp + N::ob0, x, h1);
 #pragma unroll
   for (int j = 0; j < N::H1; ++j) h1[j] = tanh_f(h1[j]);
-  dense_thread<N::H1, N::H2>(sp + N::oW1, sp + N::ob1, h1, h2);
+  if (N::H1 > 32 && hcol != nullptr) {
+#pragma unroll
+    for (int j = 0; j < N::H1; ++j) hcol[j * hld] = h1[j];
+    dense_thread_col<N::H1, N::H2>(sp + N::oW1, sp + N::ob1, hcol, hld, h2);
+  } else {
+    dense_thread<N::H1, N::H2>(sp + N::oW1, sp + N::ob1, h1, h2);
+  }
 #pragma unroll
   for (int j = 0; j < N::H2; ++j) h2[j] = tanh_f(h2[j]);
 #pragma unroll

@@ -101,7 +101,7 @@ __device__ __forceinline__ float planar_imp(float d0, float d1, float w, float r
 
 // qacc, qfrc_constraint and COM quantities at (q, v, ctrl).
 template <class M>
-__device__ __noinline__ void planar_dynamics(const float (&q)[M::nv], const float (&v)[M::nv], const float (&ctrl)[M::nu],
+__device__ __forceinline__ void planar_dynamics(const float (&q)[M::nv], const float (&v)[M::nv], const float (&ctrl)[M::nu],
                                              float (&acc)[M::nv], float (&qfc)[M::nv], PlanarKin& kin) {
   constexpr int n = M::n, nv = M::nv;
   // ---- kinematics
@@ -328,35 +328,75 @@ __device__ __noinline__ void planar_dynamics(const float (&q)[M::nv], const floa
   solve(tot, acc);
 }
 
+// Subtree COM position and the reference's body-origin "COM velocity" only (no dynamics): what obs / reward need.
+template <class M>
+__device__ __forceinline__ void planar_kin(const float (&q)[M::nv], const float (&v)[M::nv], PlanarKin& kin) {
+  constexpr int n = M::n;
+  float om[n], cs[n], sn[n];
+  {
+    float ap = 0.f, aw = 0.f;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      ap += M::sgn(i) * q[2 + i];
+      aw += M::sgn(i) * v[2 + i];
+      om[i] = aw;
+      sincosf(ap, &sn[i], &cs[i]);
+    }
+  }
+  float hx = q[M::iX], hy = q[M::iY], hdx = v[M::iX], hdy = v[M::iY];
+  float mt = 0.f, comX = 0.f, comY = 0.f, cvX = 0.f;
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    if (i > 0) {
+      const float rax = cs[i - 1] * M::ax(i) - sn[i - 1] * M::ay(i), ray = sn[i - 1] * M::ax(i) + cs[i - 1] * M::ay(i);
+      hx += rax; hy += ray;
+      hdx -= om[i - 1] * ray; hdy += om[i - 1] * rax;
+    }
+    const CapsuleC cp = M::cap(i);
+    const float rcx = cs[i] * M::cx(i) - sn[i] * M::cy(i), rcy = sn[i] * M::cx(i) + cs[i] * M::cy(i);
+    const float roy = sn[i] * M::box(i) + cs[i] * M::boy(i);
+    mt += cp.m; comX += cp.m * (hx + rcx); comY += cp.m * (hy + rcy);
+    cvX += cp.m * (hdx - om[i] * roy);
+  }
+  kin.comX = comX / mt; kin.comY = comY / mt; kin.comvelX = cvX / mt;
+}
+
+// frame_skip x (semi-implicit Euler | RK4).  RK4 is written as a 4-stage loop so that the (inlined) dynamics has a
+// single call site: y' = y + h * sum_s b_s k_s, stage state y_s = y + a_s h k_{s-1}, a = (0, 1/2, 1/2, 1), b = (1,2,2,1)/6.
 template <class M>
 __device__ __forceinline__ void planar_integrate(float (&q)[M::nv], float (&v)[M::nv], const float (&ctrl)[M::nu]) {
   constexpr int nv = M::nv;
   const float h = M::dt;
   float a[nv], qf[nv];
   PlanarKin kin;
-  for (int s = 0; s < M::frame_skip; ++s) {
-    if (!M::rk4) {
+  if (!M::rk4) {
+#pragma unroll 1
+    for (int s = 0; s < M::frame_skip; ++s) {
       planar_dynamics<M>(q, v, ctrl, a, qf, kin);
 #pragma unroll
       for (int k = 0; k < nv; ++k) { v[k] += h * a[k]; q[k] += h * v[k]; }
-    } else {
-      float k1v[nv], q2[nv], v2[nv], k2v[nv], q3[nv], v3[nv], k3v[nv], q4[nv], v4[nv], k4v[nv];
-      planar_dynamics<M>(q, v, ctrl, k1v, qf, kin);
+    }
+  } else {
+#pragma unroll 1
+    for (int s = 0; s < M::frame_skip; ++s) {
+      float qs[nv], vs[nv], sq[nv], sv_[nv];
 #pragma unroll
-      for (int k = 0; k < nv; ++k) { q2[k] = q[k] + 0.5f * h * v[k]; v2[k] = v[k] + 0.5f * h * k1v[k]; }
-      planar_dynamics<M>(q2, v2, ctrl, k2v, qf, kin);
+      for (int k = 0; k < nv; ++k) { qs[k] = q[k]; vs[k] = v[k]; sq[k] = 0.f; sv_[k] = 0.f; }
+#pragma unroll 1
+      for (int st = 0; st < 4; ++st) {
+        planar_dynamics<M>(qs, vs, ctrl, a, qf, kin);
+        const float b = (st == 0 || st == 3) ? (1.0f / 6.0f) : (1.0f / 3.0f);
+        const float an = (st == 2) ? 1.0f : 0.5f;   // coefficient of the NEXT stage
 #pragma unroll
-      for (int k = 0; k < nv; ++k) { q3[k] = q[k] + 0.5f * h * v2[k]; v3[k] = v[k] + 0.5f * h * k2v[k]; }
-      planar_dynamics<M>(q3, v3, ctrl, k3v, qf, kin);
-#pragma unroll
-      for (int k = 0; k < nv; ++k) { q4[k] = q[k] + h * v3[k]; v4[k] = v[k] + h * k3v[k]; }
-      planar_dynamics<M>(q4, v4, ctrl, k4v, qf, kin);
-      const float s6 = h / 6.0f;
-#pragma unroll
-      for (int k = 0; k < nv; ++k) {
-        q[k] += s6 * (v[k] + 2.0f * v2[k] + 2.0f * v3[k] + v4[k]);
-        v[k] += s6 * (k1v[k] + 2.0f * k2v[k] + 2.0f * k3v[k] + k4v[k]);
+        for (int k = 0; k < nv; ++k) {
+          sq[k] += b * vs[k];
+          sv_[k] += b * a[k];
+          const float nq = q[k] + an * h * vs[k], nvv = v[k] + an * h * a[k];
+          qs[k] = nq; vs[k] = nvv;
+        }
       }
+#pragma unroll
+      for (int k = 0; k < nv; ++k) { q[k] += h * sq[k]; v[k] += h * sv_[k]; }
     }
   }
 }
@@ -372,22 +412,22 @@ struct SwimmerEnvD {
     for (int k = 0; k < 5; ++k) { s[k] = M::q0(k) + 0.01f * raw[k]; s[5 + k] = 0.1f * raw[5 + k]; }
   }
   __device__ static void obs(const float (&s)[S], float (&o)[O]) {
-    float q[5], v[5], a[5], qf[5], c[2] = {0.f, 0.f};
+    float q[5], v[5];
     PlanarKin kin;
 #pragma unroll
     for (int k = 0; k < 5; ++k) { q[k] = s[k]; v[k] = s[5 + k]; }
-    planar_dynamics<M>(q, v, c, a, qf, kin);
+    planar_kin<M>(q, v, kin);
 #pragma unroll
     for (int k = 0; k < 10; ++k) o[k] = s[k];
     o[10] = kin.comX; o[11] = kin.comY; o[12] = 0.f;
   }
   __device__ static void step(float (&s)[S], const float (&u)[A], float& r, bool& done) {
-    float q[5], v[5], a[5], qf[5];
+    float q[5], v[5];
     PlanarKin kin;
 #pragma unroll
     for (int k = 0; k < 5; ++k) { q[k] = s[k]; v[k] = s[5 + k]; }
     planar_integrate<M>(q, v, u);
-    planar_dynamics<M>(q, v, u, a, qf, kin);
+    planar_kin<M>(q, v, kin);
     const float c0 = u[0] / 50.0f, c1 = u[1] / 50.0f;
     r = kin.comvelX - 0.5f * 1e-2f * (c0 * c0 + c1 * c1);
 #pragma unroll
@@ -397,32 +437,40 @@ struct SwimmerEnvD {
 };
 
 // ---------------------------------------------------------------- rllab/envs/mujoco/hopper_env.py:19-61
+// state = [qpos 6, qvel 6, ctrl 3, qfrc_constraint 6, comX, comY]: the last 8 entries cache what mj_forward leaves in
+// mjData after the step (mujoco_env.py:184-191) so that get_current_obs needs no second dynamics evaluation.
 struct HopperEnvD {
   using M = HopperModel;
-  static constexpr int KIND = B200RL_ENV_HOPPER, O = 20, A = 3, S = 15, K = 12, NOISE = B200RL_NOISE_NORMAL;
+  static constexpr int KIND = B200RL_ENV_HOPPER, O = 20, A = 3, S = 23, K = 12, NOISE = B200RL_NOISE_NORMAL;
   __host__ __device__ static constexpr float lb(int) { return -200.0f; }
   __host__ __device__ static constexpr float ub(int) { return 200.0f; }
-  __device__ static void reset(float (&s)[S], const float (&raw)[K]) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { s[k] = M::q0(k) + 0.01f * raw[k]; s[6 + k] = 0.1f * raw[6 + k]; }
-    s[12] = s[13] = s[14] = 0.f;
-  }
-  __device__ static void obs(const float (&s)[S], float (&o)[O]) {
+  __device__ __noinline__ static void forward_cache(float (&s)[S]) {   // mj_forward at the current (q, v, ctrl)
     float q[6], v[6], a[6], qf[6], c[3];
     PlanarKin kin;
 #pragma unroll
     for (int k = 0; k < 6; ++k) { q[k] = s[k]; v[k] = s[6 + k]; }
     c[0] = s[12]; c[1] = s[13]; c[2] = s[14];
     planar_dynamics<M>(q, v, c, a, qf, kin);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s[15 + k] = qf[k];
+    s[21] = kin.comX; s[22] = kin.comY;
+  }
+  __device__ static void reset(float (&s)[S], const float (&raw)[K]) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { s[k] = M::q0(k) + 0.01f * raw[k]; s[6 + k] = 0.1f * raw[6 + k]; }
+    s[12] = s[13] = s[14] = 0.f;
+    forward_cache(s);
+  }
+  __device__ static void obs(const float (&s)[S], float (&o)[O]) {
     o[0] = s[0];
 #pragma unroll
     for (int k = 0; k < 4; ++k) o[1 + k] = s[2 + k];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       o[5 + k] = fminf(fmaxf(s[6 + k], -10.f), 10.f);
-      o[11 + k] = fminf(fmaxf(qf[k], -10.f), 10.f);
+      o[11 + k] = fminf(fmaxf(s[15 + k], -10.f), 10.f);
     }
-    o[17] = kin.comX; o[18] = 0.f; o[19] = kin.comY;
+    o[17] = s[21]; o[18] = 0.f; o[19] = s[22];
   }
   __device__ static void step(float (&s)[S], const float (&u)[A], float& r, bool& done) {
     float q[6], v[6], a[6], qf[6];
@@ -443,8 +491,9 @@ struct HopperEnvD {
     }
     done = !ok;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { s[k] = q[k]; s[6 + k] = v[k]; }
+    for (int k = 0; k < 6; ++k) { s[k] = q[k]; s[6 + k] = v[k]; s[15 + k] = qf[k]; }
     s[12] = u[0]; s[13] = u[1]; s[14] = u[2];
+    s[21] = kin.comX; s[22] = kin.comY;
   }
 };
 

@@ -64,7 +64,11 @@ struct RolloutArgs {
 template <class Env, int H>
 __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(RolloutArgs a) {
   using N_ = Net<Env::O, H, H, Env::A>;
-  __shared__ __align__(16) float sp[N_::P];
+  // 32-wide: parameters only (static); 64-wide: + one activation column per thread for the rolled layer-2 loop
+  constexpr int P4 = (N_::P + 3) & ~3;
+  extern __shared__ __align__(16) float rollout_smem[];
+  float* sp = rollout_smem;
+  float* hcol = (H > 32) ? rollout_smem + P4 + threadIdx.x : nullptr;
   for (int i = threadIdx.x; i < N_::P; i += blockDim.x) sp[i] = a.params[i];
   __syncthreads();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS) rollout_kernel(RolloutArgs a)
     // compiler barrier: without it the loop-invariant LDS of all P weights is hoisted out of the t loop and spilled
     asm volatile("" ::: "memory");
     Env::obs(s, o);
-    mlp_forward_thread<N_>(sp, o, h1, h2, mu);
+    mlp_forward_thread<N_>(sp, o, h1, h2, mu, hcol, ROLLOUT_THREADS);
     draw_eps<Env::A>(e, a.eps, t, a.N, n, a.seed, a.iter, lane);
     const size_t idx = (size_t)t * N + n;
 #pragma unroll
@@ -210,9 +214,18 @@ template <class Env>
 static int launch_rollout(int h, const RolloutArgs& a, cudaStream_t st) {
   const int grid = (a.N + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
   if (h == 32) {
-    rollout_kernel<Env, 32><<<grid, ROLLOUT_THREADS, 0, st>>>(a);
+    using N32 = Net<Env::O, 32, 32, Env::A>;
+    rollout_kernel<Env, 32><<<grid, ROLLOUT_THREADS, ((N32::P + 3) & ~3) * sizeof(float), st>>>(a);
   } else if (h == 64) {
-    rollout_kernel<Env, 64><<<grid, ROLLOUT_THREADS, 0, st>>>(a);
+    using N64 = Net<Env::O, 64, 64, Env::A>;
+    const size_t smem = (((N64::P + 3) & ~3) + 64 * ROLLOUT_THREADS) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+      B200RL_CUDA_CHECK(cudaFuncSetAttribute(rollout_kernel<Env, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem));
+      attr_done = true;
+    }
+    rollout_kernel<Env, 64><<<grid, ROLLOUT_THREADS, smem, st>>>(a);
   } else {
     set_error("hidden size %d not compiled in (32 or 64)", h);
     return B200RL_EUNSUPPORTED;
