@@ -501,7 +501,8 @@ int update_impl() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("B200RL_UPDATE_IMPL");
-    cached = (e == nullptr || !strcmp(e, "gemm")) ? 0 : (!strcmp(e, "tile") ? 1 : 2);
+    // default (auto, -1): tile kernel for 32-wide nets (4 % faster there), GEMM kernel for 64-wide nets
+    cached = (e == nullptr || !strcmp(e, "auto")) ? 3 : (!strcmp(e, "gemm") ? 0 : (!strcmp(e, "tile") ? 1 : 2));
   }
   return cached;
 }
@@ -572,7 +573,8 @@ int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int
   a.obs = obs; a.act = act; a.adv = adv; a.old_mean = old_mean; a.old_log_std = old_log_std;
   a.loss_kind = loss_kind; a.partial = ws;
   int grid = 0, P = 0, ols = 0;
-  const int impl = update_impl();
+  int impl = update_impl();
+  if (impl == 3) impl = (h1 == 32) ? 1 : 0;
   if (h1 == h2 && (impl == 0 || (impl == 1 && h1 == 32))) {
     int rc = (impl == 0) ? update_gemm_launch(MODE_GRAD, obs_dim, h1, act_dim, a, &grid, &P, &ols, st)
                          : update_tile_launch(MODE_GRAD, obs_dim, act_dim, a, &grid, &P, &ols, st);
@@ -628,7 +630,8 @@ int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim
   a.params = params_f32; a.xvec = x; a.log_min_std = min_std > 0.f ? logf(min_std) : -INFINITY; a.B = B;
   a.obs = obs; a.partial = ws;
   int grid = 0, P = 0, ols = 0;
-  const int impl = update_impl();
+  int impl = update_impl();
+  if (impl == 3) impl = (h1 == 32) ? 1 : 0;
   if (h1 == h2 && (impl == 0 || (impl == 1 && h1 == 32))) {
     int rc = (impl == 0) ? update_gemm_launch(MODE_FVP, obs_dim, h1, act_dim, a, &grid, &P, &ols, st)
                          : update_tile_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st);

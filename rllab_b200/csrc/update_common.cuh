@@ -27,7 +27,8 @@ int update_tile_launch(int mode, int obs_dim, int act_dim, const UpdArgs& a, int
 int update_gemm_launch(int mode, int obs_dim, int h, int act_dim, const UpdArgs& a, int* grid_out, int* P_out,
                        int* ols_out, cudaStream_t st);
 
-// which implementation b200rl_grad / b200rl_fvp use: env B200RL_UPDATE_IMPL = gemm (default) | tile | warp
+// which implementation b200rl_grad / b200rl_fvp use: env B200RL_UPDATE_IMPL = auto (default: tile for 32-wide, gemm for
+// 64-wide nets) | gemm | tile | warp
 int update_impl();
 
 }  // namespace b200rl
