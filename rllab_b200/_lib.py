@@ -9,7 +9,7 @@ import os
 from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_uint, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb200rl.so")
+LIB_PATH = os.environ.get("B200RL_LIB") or os.path.join(_HERE, "csrc", "libb200rl.so")   # B200RL_LIB: A/B builds
 
 ENV_POINT, ENV_CARTPOLE, ENV_PENDULUM, ENV_SWIMMER, ENV_HOPPER = 0, 1, 2, 3, 4
 ENV_KINDS = dict(point=ENV_POINT, cartpole=ENV_CARTPOLE, pendulum=ENV_PENDULUM, swimmer=ENV_SWIMMER, hopper=ENV_HOPPER)

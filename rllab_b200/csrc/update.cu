@@ -397,7 +397,9 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
 // the thread-per-lane forward of the rollout kernel is the cheapest formulation; same canonical summation order).
 constexpr int LOSS_THREADS = 128;
 template <class N>
-__global__ void __launch_bounds__(LOSS_THREADS) loss_thread_kernel(UpdArgs a) {
+constexpr int loss_minblocks() { return (N::H1 == 32 && N::O <= 4) ? 4 : 1; }   // 128 registers: 1.47 -> 1.28 ms (A/B)
+template <class N>
+__global__ void __launch_bounds__(LOSS_THREADS, loss_minblocks<N>()) loss_thread_kernel(UpdArgs a) {
   constexpr int O = N::O, A = N::A;
   __shared__ __align__(16) float sp[N::P];
   __shared__ double red_scratch[3 * 32];

@@ -14,6 +14,9 @@
 namespace b200rl {
 
 constexpr int T_THREADS = 128, T_TILE = 128, T_LD = T_TILE + 4;
+#ifndef B200RL_TILE_MINBLOCKS
+#define B200RL_TILE_MINBLOCKS 2
+#endif
 
 template <class N, int MODE>
 struct TileSmem {
@@ -30,7 +33,7 @@ struct TileSmem {
 };
 
 template <class N, int MODE>
-__global__ void __launch_bounds__(T_THREADS, 2) update_tile_kernel(UpdArgs a) {
+__global__ void __launch_bounds__(T_THREADS, B200RL_TILE_MINBLOCKS) update_tile_kernel(UpdArgs a) {
   using SM = TileSmem<N, MODE>;
   constexpr int O = N::O, H = 32, A = N::A, P = N::P, LD = T_LD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
