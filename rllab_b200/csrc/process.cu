@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(PS_THREADS)
   if (n < N) {
     const size_t plane = (size_t)T * N;
     double a_next = 0.0, r_next = 0.0, u_next = 0.0, b_next = 0.0;
+#pragma unroll 4
     for (int t = T - 1; t >= 0; --t) {
       const size_t idx = (size_t)t * N + n;
       const unsigned char f = flags[idx];
@@ -167,6 +168,70 @@ __global__ void __launch_bounds__(GRAM_THREADS)
   }
 }
 
+// Small observation spaces (O <= 4, i.e. d+1 <= 13 features): the whole upper triangle (<= 91 products) fits in one
+// thread's registers, so each thread streams its samples (coalesced across the warp), accumulates the outer products
+// in float32 registers (<= ~100 samples per thread), and the block folds them once into float64 -- no shared-memory
+// staging, no bank conflicts (the staged kernel above spends its time in 13 M conflicts and LSU latency).
+template <int O>
+__global__ void __launch_bounds__(128) lfb_gram_reg_kernel(long long B, const float* __restrict__ obs,
+                                                           const unsigned short* __restrict__ tstep,
+                                                           const float* __restrict__ ret, double* __restrict__ partial) {
+  constexpr int D1 = 2 * O + 5, NP = D1 * (D1 + 1) / 2;
+  __shared__ double red[NP];
+  float acc[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) acc[p] = 0.f;
+  for (int p = threadIdx.x; p < NP; p += blockDim.x) red[p] = 0.0;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int UNR = 4;   // 4 samples' loads in flight per thread (memory-level parallelism; one is latency bound)
+  for (long long s0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; s0 < B; s0 += UNR * stride) {
+    float raw[UNR][O + 2];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long s = s0 + u * stride;
+      const bool ok = s < B;
+      const long long sl = ok ? s : s0;
+#pragma unroll
+      for (int k = 0; k < O; ++k) raw[u][k] = obs[(size_t)k * B + sl];
+      raw[u][O] = (float)tstep[sl];
+      raw[u][O + 1] = ret[sl];
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (s0 + u * stride < B) {
+        float f[D1];
+#pragma unroll
+        for (int k = 0; k < O; ++k) {
+          const float o = fminf(fmaxf(raw[u][k], -10.0f), 10.0f);
+          f[k] = o;
+          f[O + k] = o * o;
+        }
+        const float al = raw[u][O] / 100.0f;
+        f[2 * O] = al; f[2 * O + 1] = al * al; f[2 * O + 2] = al * al * al; f[2 * O + 3] = 1.0f; f[2 * O + 4] = raw[u][O + 1];
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < D1; ++i)
+#pragma unroll
+          for (int j = i; j < D1; ++j) { acc[p] = fmaf(f[i], f[j], acc[p]); ++p; }
+      }
+    }
+  }
+  // fold: warp shuffle in float64, then one shared-memory add per warp in fixed warp order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const double v = warp_sum((double)acc[p]);
+        if (lane == 0) red[p] += v;
+      }
+    }
+    __syncthreads();
+  }
+  for (int p = threadIdx.x; p < NP; p += blockDim.x) partial[(size_t)blockIdx.x * NP + p] = red[p];
+}
+
 __global__ void planes_to_rows_kernel(int dim, long long B, const float* __restrict__ src, double* __restrict__ dst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
@@ -225,6 +290,20 @@ int b200rl_lfb_gram(int obs_dim, long long B, const float* obs, const unsigned s
   if (grid > MAX_PARTIAL_BLOCKS) grid = MAX_PARTIAL_BLOCKS;
   const size_t smem = (size_t)d1 * GRAM_LD * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  if (obs_dim <= 4) {
+    long long g = (long long)num_sms() * 8;
+    const long long need = (B + 127) / 128;
+    if (g > need) g = need;
+    grid = (int)g;
+    switch (obs_dim) {
+      case 1: lfb_gram_reg_kernel<1><<<grid, 128, 0, st>>>(B, obs, tstep, ret, ws); break;
+      case 2: lfb_gram_reg_kernel<2><<<grid, 128, 0, st>>>(B, obs, tstep, ret, ws); break;
+      case 3: lfb_gram_reg_kernel<3><<<grid, 128, 0, st>>>(B, obs, tstep, ret, ws); break;
+      default: lfb_gram_reg_kernel<4><<<grid, 128, 0, st>>>(B, obs, tstep, ret, ws); break;
+    }
+    B200RL_LAUNCH_CHECK("lfb_gram_reg_kernel");
+    return launch_finalize_sum(ws, grid, npairs, gram_out, 1.0, st);
+  }
   lfb_gram_kernel<<<grid, GRAM_THREADS, smem, st>>>(obs_dim, B, obs, tstep, ret, ws);
   B200RL_LAUNCH_CHECK("lfb_gram_kernel");
   return launch_finalize_sum(ws, grid, npairs, gram_out, 1.0, st);
