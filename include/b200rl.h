@@ -142,18 +142,22 @@ int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, 
 
 /* Flat gradient of the surrogate (theano.grad in conjugate_gradient_optimizer.py:184-186 /
  * first_order_optimizer.py:62-64): g_out [P] float64 = scale * sum over samples.  loss_out (3 doubles or NULL)
- * receives the b200rl_loss_kl triple of the same pass (loss, sum kl, max kl) at no extra cost. */
+ * receives the b200rl_loss_kl triple of the same pass (loss, sum kl, max kl) at no extra cost.  h_cache_out
+ * ([h1+h2][B] float32 planes, or NULL) receives the hidden activations tanh(.) of both layers: theta is fixed during the
+ * CG solve, so the (cg_iters+1) Fisher-vector products that follow can read them back (256 B/sample of HBM traffic,
+ * ~1 % of the roofline) instead of recomputing two dense layers and 64 tanh per sample. */
 int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std,
                 long long B, const float* obs, const float* act, const float* adv, const float* old_mean,
-                const float* old_log_std, double scale, double* g_out, double* loss_out, double* ws,
-                void* stream);
+                const float* old_log_std, double scale, double* g_out, double* loss_out, float* h_cache_out,
+                double* ws, void* stream);
 
 /* Fisher/Hessian-vector product of mean KL at theta_old (PerlmutterHvp, conjugate_gradient_optimizer.py:22-55):
  * Hx_out [P] = scale * sum_samples J^T M J x  (+ reg_coeff*x and the log_std block added once: pass
- * add_diag=1 on exactly one rank, or on all ranks with diag_scale = 1/world_size). */
+ * add_diag=1 on exactly one rank, or on all ranks with diag_scale = 1/world_size).  h_cache: activations written by
+ * b200rl_grad at the SAME parameters, or NULL to recompute them. */
 int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std, long long B,
                const float* obs, const double* x, double scale, double reg_coeff, double diag_scale, double* Hx_out,
-               double* ws, void* stream);
+               const float* h_cache, double* ws, void* stream);
 
 /* Workspace size (float64 entries) sufficient for every reduction above on the current device. */
 long long b200rl_ws_doubles(void);

@@ -44,9 +44,9 @@ SIGNATURES = {
     "b200rl_loss_kl": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, _P, _P, _P, c_double, _P,
                                _P, _P]),
     "b200rl_grad": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, _P, _P, _P, c_double, _P, _P,
-                            _P, _P]),
+                            _P, _P, _P]),
     "b200rl_fvp": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, c_double, c_double, c_double, _P, _P,
-                           _P]),
+                           _P, _P]),
     "b200rl_ws_doubles": (_LL, []),
     "b200rl_cg_init": (c_int, [_LL, _P, _P, _P, _P, _P, _P]),
     "b200rl_cg_step": (c_int, [_LL, _P, _P, _P, _P, _P, c_double, _P]),

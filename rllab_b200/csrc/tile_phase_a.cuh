@@ -35,12 +35,19 @@ __device__ __forceinline__ void tile_phase_a(const UpdArgs& a, const float* sp, 
       x[o] = a.obs[(size_t)o * a.B + sl];
       colX[o * LD] = x[o];
     }
-    dense_thread<O, H>(sp + N::oW0, sp + N::ob0, x, h1);
+    // activation cache (theta is fixed between the gradient and the CG solve): GRAD writes tanh outputs, FVP reads them
+    const bool cached = (MODE == MODE_FVP) && (a.h_cache != nullptr);
+    float* hc = a.h_cache ? a.h_cache + sl : nullptr;
+    if (cached) {
 #pragma unroll
-    for (int j = 0; j < H; ++j) {
-      h1[j] = tanh_f(h1[j]);
-      colH1[j * LD] = h1[j];
+      for (int j = 0; j < H; ++j) h1[j] = hc[(size_t)j * a.B];
+    } else {
+      dense_thread<O, H>(sp + N::oW0, sp + N::ob0, x, h1);
+#pragma unroll
+      for (int j = 0; j < H; ++j) h1[j] = tanh_f(h1[j]);
     }
+#pragma unroll
+    for (int j = 0; j < H; ++j) colH1[j * LD] = h1[j];
     if constexpr (MODE == MODE_FVP) {
       // h1 V1 -> parked in the D1 rows
       float p2b[H];
@@ -50,11 +57,22 @@ __device__ __forceinline__ void tile_phase_a(const UpdArgs& a, const float* sp, 
       B200RL_SECTION_BARRIER();
     }
     float h2[H];
-    dense_thread<H, H>(sp + N::oW1, sp + N::ob1, h1, h2);
+    if (cached) {
 #pragma unroll
-    for (int j = 0; j < H; ++j) {
-      h2[j] = tanh_f(h2[j]);
-      colH2[j * LD] = h2[j];
+      for (int j = 0; j < H; ++j) h2[j] = hc[(size_t)(H + j) * a.B];
+    } else {
+      dense_thread<H, H>(sp + N::oW1, sp + N::ob1, h1, h2);
+#pragma unroll
+      for (int j = 0; j < H; ++j) h2[j] = tanh_f(h2[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) colH2[j * LD] = h2[j];
+    if (MODE == MODE_GRAD && hc != nullptr && valid) {
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        hc[(size_t)j * a.B] = colH1[j * LD];
+        hc[(size_t)(H + j) * a.B] = h2[j];
+      }
     }
     B200RL_SECTION_BARRIER();
     if constexpr (MODE == MODE_GRAD) {

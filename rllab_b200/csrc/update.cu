@@ -565,7 +565,8 @@ int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, 
 
 int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std,
                 long long B, const float* obs, const float* act, const float* adv, const float* old_mean,
-                const float* old_log_std, double scale, double* g_out, double* loss_out, double* ws, void* stream) {
+                const float* old_log_std, double scale, double* g_out, double* loss_out, float* h_cache_out, double* ws,
+                void* stream) {
   B200RL_REQUIRE(params_f32 && obs && act && adv && old_mean && old_log_std && g_out && ws && B > 0,
                  "grad: bad arguments");
   B200RL_REQUIRE(loss_kind == B200RL_LOSS_TRPO || loss_kind == B200RL_LOSS_VPG, "grad: bad loss kind");
@@ -573,7 +574,7 @@ int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int
   UpdArgs a{};
   a.params = params_f32; a.log_min_std = min_std > 0.f ? logf(min_std) : -INFINITY; a.B = B;
   a.obs = obs; a.act = act; a.adv = adv; a.old_mean = old_mean; a.old_log_std = old_log_std;
-  a.loss_kind = loss_kind; a.partial = ws;
+  a.loss_kind = loss_kind; a.partial = ws; a.h_cache = h_cache_out;
   int grid = 0, P = 0, ols = 0;
   int impl = update_impl();
   if (impl == 3) impl = (h1 == 32) ? 1 : 0;
@@ -625,12 +626,12 @@ int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int
 
 int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std, long long B,
                const float* obs, const double* x, double scale, double reg_coeff, double diag_scale, double* Hx_out,
-               double* ws, void* stream) {
+               const float* h_cache, double* ws, void* stream) {
   B200RL_REQUIRE(params_f32 && obs && x && Hx_out && ws && B > 0, "fvp: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   UpdArgs a{};
   a.params = params_f32; a.xvec = x; a.log_min_std = min_std > 0.f ? logf(min_std) : -INFINITY; a.B = B;
-  a.obs = obs; a.partial = ws;
+  a.obs = obs; a.partial = ws; a.h_cache = const_cast<float*>(h_cache);
   int grid = 0, P = 0, ols = 0;
   int impl = update_impl();
   if (impl == 3) impl = (h1 == 32) ? 1 : 0;

@@ -10,6 +10,7 @@ constexpr int MODE_LOSS = 0, MODE_GRAD = 1, MODE_FVP = 2;
 struct UpdArgs {
   const float* params;
   const double* xvec;  // FVP: tangent vector (float64, P)
+  float* h_cache;      // [H1+H2][B] hidden activations: written by GRAD (if non-null), read by FVP (if non-null)
   float log_min_std;
   long long B;
   const float *obs, *act, *adv, *old_mean, *old_log_std;

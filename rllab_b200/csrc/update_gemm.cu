@@ -95,6 +95,33 @@ __device__ __forceinline__ void store_tanh_tile(const float2 (&ae)[4][RJ], const
     *reinterpret_cast<float4*>(dst + c * G_LD + 4) = make_float4(v[4], v[5], v[6], v[7]);
   }
 }
+// activation cache <-> staged tile (RJ rows x 8 samples starting at sample index sbase; rows are B apart in the cache)
+template <int RJ>
+__device__ __forceinline__ void load_cached_tile(const float* src, long long B, long long sbase, float* dst) {
+#pragma unroll
+  for (int c = 0; c < RJ; ++c) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const long long s = sbase + e;
+      v[e] = src[(size_t)c * B + (s < B ? s : B - 1)];
+    }
+    *reinterpret_cast<float4*>(dst + c * G_LD) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + c * G_LD + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+template <int RJ>
+__device__ __forceinline__ void save_cached_tile(const float* src, float* dst, long long B, long long sbase) {
+#pragma unroll
+  for (int c = 0; c < RJ; ++c) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const long long s = sbase + e;
+      if (s < B) dst[(size_t)c * B + s] = src[c * G_LD + e];
+    }
+  }
+}
+
 // dst = (ae + ao) * (1 - h^2) with h read back from this thread's own tile of the staged activation rows
 template <int RJ>
 __device__ __forceinline__ void store_scaled_tile(const float2 (&ae)[4][RJ], const float2 (&ao)[4][RJ],
@@ -247,9 +274,15 @@ __global__ void __launch_bounds__(G_THREADS, (N::H1 == 32 ? 2 : 1)) update_gemm_
     // ---- S1: H1 = tanh(W0^T X + b0)   (and, FVP, T1 = (1-H1^2)(V0^T X + vb0) -> D1 rows)
     {
       float2 ae[4][RJ], ao[4][RJ];
-      acc_init<RJ>(ae, ao, sp + N::ob0, j0);
-      gemm_acc<O, H, RJ>(stage + SM::rX * LD, sp + N::oW0, s0, j0, ae, ao);
-      store_tanh_tile<RJ>(ae, ao, stage + (SM::rH1 + j0) * LD + s0);
+      if (MODE == MODE_FVP && a.h_cache != nullptr) {
+        load_cached_tile<RJ>(a.h_cache + (size_t)j0 * a.B, a.B, tile * G_TS + s0, stage + (SM::rH1 + j0) * LD + s0);
+      } else {
+        acc_init<RJ>(ae, ao, sp + N::ob0, j0);
+        gemm_acc<O, H, RJ>(stage + SM::rX * LD, sp + N::oW0, s0, j0, ae, ao);
+        store_tanh_tile<RJ>(ae, ao, stage + (SM::rH1 + j0) * LD + s0);
+        if (MODE == MODE_GRAD && a.h_cache != nullptr)
+          save_cached_tile<RJ>(stage + (SM::rH1 + j0) * LD + s0, a.h_cache + (size_t)j0 * a.B, a.B, tile * G_TS + s0);
+      }
       if constexpr (MODE == MODE_FVP) {
         acc_init<RJ>(ae, ao, sv + N::ob0, j0);
         gemm_acc<O, H, RJ>(stage + SM::rX * LD, sv + N::oW0, s0, j0, ae, ao);
@@ -260,9 +293,15 @@ __global__ void __launch_bounds__(G_THREADS, (N::H1 == 32 ? 2 : 1)) update_gemm_
     // ---- S2: H2 = tanh(W1^T H1 + b1)   (and, FVP, T2 = (1-H2^2)(W1^T T1 + V1^T H1 + vb1) -> D2 rows)
     {
       float2 ae[4][RJ], ao[4][RJ];
-      acc_init<RJ>(ae, ao, sp + N::ob1, j0);
-      gemm_acc<H, H, RJ>(stage + SM::rH1 * LD, sp + N::oW1, s0, j0, ae, ao);
-      store_tanh_tile<RJ>(ae, ao, stage + (SM::rH2 + j0) * LD + s0);
+      if (MODE == MODE_FVP && a.h_cache != nullptr) {
+        load_cached_tile<RJ>(a.h_cache + (size_t)(H + j0) * a.B, a.B, tile * G_TS + s0, stage + (SM::rH2 + j0) * LD + s0);
+      } else {
+        acc_init<RJ>(ae, ao, sp + N::ob1, j0);
+        gemm_acc<H, H, RJ>(stage + SM::rH1 * LD, sp + N::oW1, s0, j0, ae, ao);
+        store_tanh_tile<RJ>(ae, ao, stage + (SM::rH2 + j0) * LD + s0);
+        if (MODE == MODE_GRAD && a.h_cache != nullptr)
+          save_cached_tile<RJ>(stage + (SM::rH2 + j0) * LD + s0, a.h_cache + (size_t)(H + j0) * a.B, a.B, tile * G_TS + s0);
+      }
       if constexpr (MODE == MODE_FVP) {
         acc_init<RJ>(ae, ao, sv + N::ob1, j0);
         gemm_acc<H, H, RJ>(stage + SM::rD1 * LD, sp + N::oW1, s0, j0, ae, ao);   // T1 W1

@@ -68,6 +68,14 @@ class LaneBatch(object):
     def B(self):
         return self.N * self.T
 
+    def hcache(self, h1, h2):
+        """[h1+h2][T][N] float32 activation cache for the CG solve (allocated on first use; 256 B/sample at 32,32)."""
+        hc = getattr(self, "_hcache", None)
+        if hc is None or hc.shape[0] != h1 + h2:
+            hc = torch.empty((h1 + h2, self.T, self.N), dtype=F32, device=self.device)
+            self._hcache = hc
+        return hc
+
     def to_numpy(self):
         """Host copy in the oracle's dict layout (tests / path materialisation)."""
         return dict(obs=self.obs.cpu().numpy(), act=self.act.cpu().numpy(), mean=self.mean.cpu().numpy(),
@@ -139,21 +147,22 @@ def loss_kl(loss_kind, params32, dims, min_std, batch, scale, out):
            L.ptr(workspace(b.device)), _stream())
 
 
-def grad(loss_kind, params32, dims, min_std, batch, scale, g_out, loss_out=None):
+def grad(loss_kind, params32, dims, min_std, batch, scale, g_out, loss_out=None, h_cache=None):
     O, h1, h2, A = dims
     b = batch
     _chk(params32, F32, "params32"), _chk(g_out, F64, "g_out")
     L.call("b200rl_grad", loss_kind, L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
            L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), float(scale), L.ptr(g_out), L.ptr(loss_out),
-           L.ptr(workspace(b.device)), _stream())
+           L.ptr(h_cache), L.ptr(workspace(b.device)), _stream())
 
 
-def fvp(params32, dims, min_std, batch, x, scale, reg_coeff, diag_scale, Hx_out):
+def fvp(params32, dims, min_std, batch, x, scale, reg_coeff, diag_scale, Hx_out, h_cache=None):
     O, h1, h2, A = dims
     b = batch
     _chk(params32, F32, "params32"), _chk(x, F64, "x"), _chk(Hx_out, F64, "Hx_out", x.numel())
     L.call("b200rl_fvp", L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs), L.ptr(x),
-           float(scale), float(reg_coeff), float(diag_scale), L.ptr(Hx_out), L.ptr(workspace(b.device)), _stream())
+           float(scale), float(reg_coeff), float(diag_scale), L.ptr(Hx_out), L.ptr(h_cache), L.ptr(workspace(b.device)),
+           _stream())
 
 
 def cg_init(g, x, r, p, st):

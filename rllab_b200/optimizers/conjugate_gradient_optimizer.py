@@ -16,7 +16,8 @@ from ..misc import logger
 
 class ConjugateGradientOptimizer(object):
     def __init__(self, cg_iters=10, reg_coeff=1e-5, subsample_factor=1., backtrack_ratio=0.8, max_backtracks=15,
-                 accept_violation=False, hvp_approach=None, num_slices=1, residual_tol=1e-10):
+                 accept_violation=False, hvp_approach=None, num_slices=1, residual_tol=1e-10,
+                 use_activation_cache=True):
         if subsample_factor != 1.:
             raise NotImplementedError("subsample_factor < 1 (conjugate_gradient_optimizer.py:235-245) is not on the "
                                       "B200 hot path yet")
@@ -36,10 +37,12 @@ class ConjugateGradientOptimizer(object):
         self._bufs = None
         self._cache = None     # (policy version, batch id) -> (loss, mean_kl, max_kl)
         self._g_key = None     # key for which the `g` buffer holds the flat gradient
+        self._hc_key = None    # key for which the batch's activation cache is valid
+        self._use_hcache = use_activation_cache
         self.last_info = {}
 
     def __getstate__(self):
-        return _drop_device_state(self.__dict__, ("_bufs", "_cache", "_g_key", "_comm"))
+        return _drop_device_state(self.__dict__, ("_bufs", "_cache", "_g_key", "_hc_key", "_comm"))
 
     def update_opt(self, loss, target, leq_constraint, inputs=None, extra_inputs=None, constraint_name="constraint",
                    comm=None, *args, **kwargs):
@@ -75,7 +78,10 @@ class ConjugateGradientOptimizer(object):
             return self._cache[1]
         b = self._buffers(pol.n_params, batch.device)
         if want_grad:
-            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, b["g"], b["out"])
+            hc = batch.hcache(pol.h1, pol.h2) if self._use_hcache else None
+            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, b["g"], b["out"],
+                     hc)
+            self._hc_key = key if hc is not None else None
             if self._comm is not None and self._comm.active:
                 self._comm.all_reduce_sum(b["g"])
             self._g_key = key
@@ -107,12 +113,16 @@ class ConjugateGradientOptimizer(object):
         loss_before = self._eval(batch, want_grad=True)[0]
         logger.log("performing update")
         logger.log("computing descent direction")
-        if self._g_key != (pol.version, id(batch), batch.version):
-            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, scale, b["g"])
+        key0 = (pol.version, id(batch), batch.version)
+        if self._g_key != key0:
+            hc0 = batch.hcache(pol.h1, pol.h2) if self._use_hcache else None
+            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, scale, b["g"], None, hc0)
+            self._hc_key = key0 if hc0 is not None else None
             ar(b["g"])
+        hcache = batch.hcache(pol.h1, pol.h2) if (self._use_hcache and self._hc_key == key0) else None
 
         def Hx(vec, out):
-            ops.fvp(pol.theta32, pol.dims, pol.min_std, batch, vec, scale, self._reg_coeff, 1.0 / world, out)
+            ops.fvp(pol.theta32, pol.dims, pol.min_std, batch, vec, scale, self._reg_coeff, 1.0 / world, out, hcache)
             ar(out)
 
         ops.cg_init(b["g"], b["x"], b["r"], b["p"], b["st"])

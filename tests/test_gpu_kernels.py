@@ -360,6 +360,13 @@ def test_loss_kl_grad_fvp_match_oracle(dev, env_name, hidden):
     xd = torch.tensor(x, dtype=torch.float64, device=dev)
     Hx = torch.zeros(dims.P, dtype=torch.float64, device=dev)
     ops.fvp(th32, dd, 1e-6, b, xd, 1.0 / B, 1e-5, 1.0, Hx)
+    # activation cache: the gradient pass at theta_old stores tanh outputs, the FVP reads them back -> identical result
+    hc = b.hcache(hidden, hidden)
+    gtmp = torch.zeros(dims.P, dtype=torch.float64, device=dev)
+    ops.grad(L.LOSS_TRPO, th32, dd, 1e-6, b, 1.0 / B, gtmp, None, hc)
+    Hx_c = torch.zeros(dims.P, dtype=torch.float64, device=dev)
+    ops.fvp(th32, dd, 1e-6, b, xd, 1.0 / B, 1e-5, 1.0, Hx_c, hc)
+    np.testing.assert_allclose(Hx_c.cpu().numpy(), Hx.cpu().numpy(), rtol=1e-12, atol=1e-18)
     x32 = x.astype(np.float32).astype(np.float64)          # the kernel rounds the tangent to float32
     ref_Hx = P.fvp(theta, batch, x32, dims, 0.0) + 1e-5 * x
     np.testing.assert_allclose(Hx.cpu().numpy(), ref_Hx, rtol=2e-4, atol=2e-6 * np.abs(ref_Hx).max())
