@@ -47,30 +47,52 @@ __global__ void __launch_bounds__(PS_THREADS)
   if (n < N) {
     const size_t plane = (size_t)T * N;
     double a_next = 0.0, r_next = 0.0, u_next = 0.0, b_next = 0.0;
-#pragma unroll 4
-    for (int t = T - 1; t >= 0; --t) {
-      const size_t idx = (size_t)t * N + n;
-      const unsigned char f = flags[idx];
-      const unsigned short ts = tstep[idx];
-      const double r = (double)rew[idx];
-      const double b = have_w ? lfb_predict(obs, plane, idx, O, ts, sw) : 0.0;
-      if (f & B200RL_FLAG_END) { a_next = 0.0; r_next = 0.0; u_next = 0.0; b_next = 0.0; }
-      const double delta = r + discount * b_next - b;   // base.py:59-61
-      a_next = delta + gl * a_next;                      // discount_cumsum(deltas, discount*lambda)
-      r_next = r + discount * r_next;                    // discount_cumsum(rewards, discount)
-      u_next = r + u_next;
-      b_next = b;
-      const float af = (float)a_next, rf = (float)r_next, bf = (float)b;
-      adv[idx] = af; ret[idx] = rf; base[idx] = bf;
-      // statistics use the float64 values (as the reference does)
-      s[0] += a_next; s[1] += a_next * a_next; s[2] += 1.0;
-      s[7] += r_next; s[8] += r_next * r_next; s[9] += b; s[10] += b * b;
-      const double res = r_next - b;
-      s[11] += res; s[12] += res * res;
-      m[2] = fmax(m[2], -a_next); m[3] = fmax(m[3], a_next);
-      if (ts == 0) {  // first sample of a path
-        s[3] += 1.0; s[4] += r_next; s[5] += u_next; s[6] += u_next * u_next;
-        m[0] = fmax(m[0], u_next); m[1] = fmax(m[1], -u_next);
+    // The recurrences are sequential in t but the loads are not: fetch CH steps ahead of the arithmetic so that CH
+    // (x up to O+3) independent loads are in flight per thread (the naive loop is long-scoreboard bound, ncu r01b).
+    constexpr int CH = 4;
+    for (int tb = T - 1; tb >= 0; tb -= CH) {
+      unsigned char fl[CH];
+      unsigned short tsv[CH];
+      float rw[CH];
+      double bs[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int t = tb - u;
+        const size_t idx = (size_t)(t >= 0 ? t : 0) * N + n;
+        fl[u] = flags[idx]; tsv[u] = tstep[idx]; rw[u] = rew[idx];
+      }
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int t = tb - u;
+        const size_t idx = (size_t)(t >= 0 ? t : 0) * N + n;
+        bs[u] = have_w ? lfb_predict(obs, plane, idx, O, tsv[u], sw) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int t = tb - u;
+        if (t < 0) break;
+        const size_t idx = (size_t)t * N + n;
+        const unsigned char f = fl[u];
+        const unsigned short ts = tsv[u];
+        const double r = (double)rw[u];
+        const double b = bs[u];
+        if (f & B200RL_FLAG_END) { a_next = 0.0; r_next = 0.0; u_next = 0.0; b_next = 0.0; }
+        const double delta = r + discount * b_next - b;   // base.py:59-61
+        a_next = delta + gl * a_next;                      // discount_cumsum(deltas, discount*lambda)
+        r_next = r + discount * r_next;                    // discount_cumsum(rewards, discount)
+        u_next = r + u_next;
+        b_next = b;
+        adv[idx] = (float)a_next; ret[idx] = (float)r_next; base[idx] = (float)b;
+        // statistics use the float64 values (as the reference does)
+        s[0] += a_next; s[1] += a_next * a_next; s[2] += 1.0;
+        s[7] += r_next; s[8] += r_next * r_next; s[9] += b; s[10] += b * b;
+        const double res = r_next - b;
+        s[11] += res; s[12] += res * res;
+        m[2] = fmax(m[2], -a_next); m[3] = fmax(m[3], a_next);
+        if (ts == 0) {  // first sample of a path
+          s[3] += 1.0; s[4] += r_next; s[5] += u_next; s[6] += u_next * u_next;
+          m[0] = fmax(m[0], u_next); m[1] = fmax(m[1], -u_next);
+        }
       }
     }
   }

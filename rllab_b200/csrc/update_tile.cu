@@ -14,9 +14,7 @@
 namespace b200rl {
 
 constexpr int T_THREADS = 128, T_TILE = 128, T_LD = T_TILE + 4;
-#ifndef B200RL_TILE_MINBLOCKS
-#define B200RL_TILE_MINBLOCKS 2
-#endif
+
 
 template <class N, int MODE>
 struct TileSmem {
@@ -32,8 +30,13 @@ struct TileSmem {
   static_assert(2 * 64 * 16 * 8 <= R * T_LD * 4, "stage region must hold the K-half combine scratch");
 };
 
+// Resident CTAs per SM: 3 when three tiles fit the 228 KB of shared memory (small O, A: CartPole / Pendulum / PointEnv
+// gradient -> 168 registers, 12 warps/SM: 3.88 -> 3.44 ms on cfg2, A/B measured), otherwise 2 (<= 255 registers).
 template <class N, int MODE>
-__global__ void __launch_bounds__(T_THREADS, B200RL_TILE_MINBLOCKS) update_tile_kernel(UpdArgs a) {
+constexpr int tile_minblocks() { return (TileSmem<N, MODE>::bytes + 1024) * 3 <= 228 * 1024 ? 3 : 2; }
+
+template <class N, int MODE>
+__global__ void __launch_bounds__(T_THREADS, tile_minblocks<N, MODE>()) update_tile_kernel(UpdArgs a) {
   using SM = TileSmem<N, MODE>;
   constexpr int O = N::O, H = 32, A = N::A, P = N::P, LD = T_LD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -221,9 +224,9 @@ static int launch_tile(const UpdArgs& a, int* grid_out, cudaStream_t st) {
                                            (int)SM::bytes));
     attr_done = true;
   }
-  int per_sm = (int)((227 * 1024) / (SM::bytes + 1024));
+  int per_sm = (int)((228 * 1024) / (SM::bytes + 1024));   // 228 KB per SM, 1 KB reserved per resident CTA
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 3) per_sm = 3;
+  if (per_sm > tile_minblocks<N, MODE>()) per_sm = tile_minblocks<N, MODE>();
   long long grid = (long long)num_sms() * per_sm;
   const long long ntiles = (a.B + T_TILE - 1) / T_TILE;
   if (grid > ntiles) grid = ntiles;

@@ -36,6 +36,7 @@ class GaussianMLPPolicy(object):
         self._dist = dist_cls(self.action_dim)
         self._theta64 = None
         self._theta32 = None
+        self._pin = None
         self.version = 0          # bumped whenever the parameters change (optimizers cache loss/KL per version)
         rng = np.random if seed is None else np.random.RandomState(seed)
         self._host_init = self._init_values(rng, init_std)
@@ -96,7 +97,10 @@ class GaussianMLPPolicy(object):
             self._host_init = flat.copy()
             return
         import torch
-        self._theta64.copy_(torch.as_tensor(flat))
+        if getattr(self, "_pin", None) is None:
+            self._pin = torch.empty(self.n_params, dtype=torch.float64).pin_memory()   # page-locked staging buffer
+        self._pin.copy_(torch.as_tensor(flat))
+        self._theta64.copy_(self._pin, non_blocking=True)
         self._theta32.copy_(self._theta64)            # value.astype(dtype), parameterized.py:68
 
     def get_param_shapes(self, **tags):
