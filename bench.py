@@ -278,8 +278,13 @@ def main():
         v["share_of_step"] = v["ms"] * v["per_iter"] / (ms_dev / args.steps)
     dom = max(kern, key=lambda k: kern[k]["ms"] * kern[k]["per_iter"])
     peak, peak_src = measured_peaks()
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this exact
+    # workload (profiles/r01b_ncu_summary.md); only quoted when the workload geometry is the profiled one
+    NCU_TRAFFIC = {("cartpole_vpg_65536x200", "grad"): 3.71e8, ("cartpole_vpg_65536x200", "rollout"): 3.48e8,
+                   ("cartpole_vpg_65536x200", "loss_kl"): 3.71e8, ("cartpole_vpg_65536x200", "process_samples"): 4.31e8}
+    traffic = NCU_TRAFFIC.get((args.workload, dom)) if (args.lanes is None and args.horizon is None) else None
     roofline = dict(bound="hbm", kernel=dom, achieved=kern[dom]["GBps"], peak=peak, unit="GB/s",
-                    frac=kern[dom]["GBps"] / peak, traffic=None, peak_source=peak_src,
+                    frac=kern[dom]["GBps"] / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=kern[dom]["bytes"], launch_ms=kern[dom]["ms"],
                     note="per-kernel CUDA-event times of this run; the policy passes are FP32-issue bound, not HBM "
                          "bound (DESIGN.md 'Rooflines')")

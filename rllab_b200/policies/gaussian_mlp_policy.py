@@ -70,6 +70,7 @@ class GaussianMLPPolicy(object):
             dev = torch.device("cuda", torch.cuda.current_device())
             self._theta64 = torch.as_tensor(self._host_init, dtype=torch.float64).to(dev)
             self._theta32 = self._theta64.to(torch.float32)
+            self._pin = torch.empty(self.n_params, dtype=torch.float64).pin_memory()   # page-locked H2D staging
         return self._theta64, self._theta32
 
     @property
