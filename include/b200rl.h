@@ -159,6 +159,16 @@ int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim
                const float* obs, const double* x, double scale, double reg_coeff, double diag_scale, double* Hx_out,
                const float* h_cache, double* ws, void* stream);
 
+/* float64 "parity mode" of the three passes above on the float64 master parameters (mode 0 = loss/KL -> loss_out[3],
+ * 1 = gradient -> vec_out[P] (+ loss_out[3] if non-NULL), 2 = Fisher-vector product of x -> vec_out[P]).  The reference's
+ * default floatX is float64; with cg_iters = 10 the CG recursion amplifies float32 rounding of the Hessian-vector
+ * product past any useful tolerance (DESIGN.md "Parity limit"), so this mode exists to compare the whole TRPO step
+ * with the oracle at the reference's default settings.  ~10x slower than the float32 kernels. */
+int b200rl_update_f64(int mode, int loss_kind, const double* params_f64, int obs_dim, int h1, int h2, int act_dim,
+                      double min_std, long long B, const float* obs, const float* act, const float* adv,
+                      const float* old_mean, const float* old_log_std, const double* x, double scale, double reg_coeff,
+                      double diag_scale, double* vec_out, double* loss_out, double* ws, void* stream);
+
 /* Workspace size (float64 entries) sufficient for every reduction above on the current device. */
 long long b200rl_ws_doubles(void);
 

@@ -47,6 +47,8 @@ SIGNATURES = {
                             _P, _P, _P]),
     "b200rl_fvp": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, c_double, c_double, c_double, _P, _P,
                            _P, _P]),
+    "b200rl_update_f64": (c_int, [c_int, c_int, _P, c_int, c_int, c_int, c_int, c_double, _LL, _P, _P, _P, _P, _P, _P,
+                                  c_double, c_double, c_double, _P, _P, _P, _P]),
     "b200rl_ws_doubles": (_LL, []),
     "b200rl_cg_init": (c_int, [_LL, _P, _P, _P, _P, _P, _P]),
     "b200rl_cg_step": (c_int, [_LL, _P, _P, _P, _P, _P, c_double, _P]),

@@ -165,6 +165,16 @@ def fvp(params32, dims, min_std, batch, x, scale, reg_coeff, diag_scale, Hx_out,
            _stream())
 
 
+def update_f64(mode, loss_kind, params64, dims, min_std, batch, x, scale, reg_coeff, diag_scale, vec_out, loss_out):
+    """float64 parity-mode pass: mode 0 loss/KL, 1 gradient (+loss), 2 Fisher-vector product."""
+    O, h1, h2, A = dims
+    b = batch
+    _chk(params64, F64, "params64"), _chk(x, F64, "x"), _chk(vec_out, F64, "vec_out"), _chk(loss_out, F64, "loss_out", 3)
+    L.call("b200rl_update_f64", mode, loss_kind, L.ptr(params64), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
+           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), L.ptr(x), float(scale), float(reg_coeff),
+           float(diag_scale), L.ptr(vec_out), L.ptr(loss_out), L.ptr(workspace(b.device)), _stream())
+
+
 def cg_init(g, x, r, p, st):
     L.call("b200rl_cg_init", g.numel(), L.ptr(g), L.ptr(x), L.ptr(r), L.ptr(p), L.ptr(st), _stream())
 

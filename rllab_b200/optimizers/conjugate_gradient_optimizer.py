@@ -17,7 +17,7 @@ from ..misc import logger
 class ConjugateGradientOptimizer(object):
     def __init__(self, cg_iters=10, reg_coeff=1e-5, subsample_factor=1., backtrack_ratio=0.8, max_backtracks=15,
                  accept_violation=False, hvp_approach=None, num_slices=1, residual_tol=1e-10,
-                 use_activation_cache=True):
+                 use_activation_cache=True, precision="f32"):
         if subsample_factor != 1.:
             raise NotImplementedError("subsample_factor < 1 (conjugate_gradient_optimizer.py:235-245) is not on the "
                                       "B200 hot path yet")
@@ -38,7 +38,10 @@ class ConjugateGradientOptimizer(object):
         self._cache = None     # (policy version, batch id) -> (loss, mean_kl, max_kl)
         self._g_key = None     # key for which the `g` buffer holds the flat gradient
         self._hc_key = None    # key for which the batch's activation cache is valid
-        self._use_hcache = use_activation_cache
+        self._use_hcache = use_activation_cache and precision == "f32"
+        if precision not in ("f32", "f64"):
+            raise ValueError("precision must be 'f32' (fast path) or 'f64' (parity mode)")
+        self._f64 = precision == "f64"
         self.last_info = {}
 
     def __getstate__(self):
@@ -77,7 +80,14 @@ class ConjugateGradientOptimizer(object):
         if self._cache is not None and self._cache[0] == key:
             return self._cache[1]
         b = self._buffers(pol.n_params, batch.device)
-        if want_grad:
+        if self._f64:
+            ops.update_f64(1 if want_grad else 0, self._loss_kind, pol.theta64, pol.dims, pol.min_std, batch, None,
+                           1.0 / batch.B_global, 0.0, 0.0, b["g"] if want_grad else None, b["out"])
+            if want_grad:
+                if self._comm is not None and self._comm.active:
+                    self._comm.all_reduce_sum(b["g"])
+                self._g_key = key
+        elif want_grad:
             hc = batch.hcache(pol.h1, pol.h2) if self._use_hcache else None
             ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, b["g"], b["out"],
                      hc)
@@ -114,6 +124,11 @@ class ConjugateGradientOptimizer(object):
         logger.log("performing update")
         logger.log("computing descent direction")
         key0 = (pol.version, id(batch), batch.version)
+        if self._g_key != key0 and self._f64:
+            ops.update_f64(1, self._loss_kind, pol.theta64, pol.dims, pol.min_std, batch, None, scale, 0.0, 0.0,
+                           b["g"], None)
+            ar(b["g"])
+            self._g_key = key0
         if self._g_key != key0:
             hc0 = batch.hcache(pol.h1, pol.h2) if self._use_hcache else None
             ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, scale, b["g"], None, hc0)
@@ -122,6 +137,11 @@ class ConjugateGradientOptimizer(object):
         hcache = batch.hcache(pol.h1, pol.h2) if (self._use_hcache and self._hc_key == key0) else None
 
         def Hx(vec, out):
+            if self._f64:
+                ops.update_f64(2, self._loss_kind, pol.theta64, pol.dims, pol.min_std, batch, vec, scale,
+                               self._reg_coeff, 1.0 / world, out, None)
+                ar(out)
+                return
             ops.fvp(pol.theta32, pol.dims, pol.min_std, batch, vec, scale, self._reg_coeff, 1.0 / world, out, hcache)
             ar(out)
 

@@ -269,3 +269,28 @@ def test_snapshot_and_resume(dev, algo_name, tmp_path):
     rel = np.max(np.abs(resumed.policy.get_param_values() - algo3.policy.get_param_values())) / \
         np.max(np.abs(algo3.policy.get_param_values()))
     assert rel < 1e-12, rel
+
+
+@pytest.mark.parametrize("env_name,hidden", [("cartpole", 32), ("point", 32), ("cartpole", 64)])
+def test_trpo_f64_mode_matches_oracle_at_default_cg_iters(dev, env_name, hidden):
+    """precision="f64": the whole TRPO step at the reference's DEFAULT settings (cg_iters=10, reg 1e-5, 15 backtracks)
+    against the float64 oracle on the same batch -- parameters within 1e-5 relative, same line-search index."""
+    algo = _algo(env_name, "trpo", 1024, 50, hidden, optimizer_args=dict(cg_iters=10, precision="f64"))
+    algo.start_worker()
+    algo.init_opt()
+    paths = algo.sampler.obtain_samples(0)
+    sd = algo.sampler.process_samples(0, paths)
+    b = sd.lane_batch
+    theta0 = algo.policy.get_param_values()                     # float64 master parameters
+    batch = S.batch_from_traj(b.to_numpy(), b.adv.cpu().numpy())
+    dims = P.Dims(b.O, (hidden, hidden), b.A)
+    algo.optimize_policy(0, sd)
+    theta_dev = algo.policy.get_param_values()
+    theta_ref, info = OPT.trpo_step(theta0, batch, dims, step_size=0.01, cg_iters=10)
+    li = algo.optimizer.last_info
+    assert li["n_iter"] == info["n_iter"] and li["rejected"] == info["rejected"] and not info["rejected"]
+    assert _rel(theta_dev, theta_ref) < PARAM_RTOL, _rel(theta_dev, theta_ref)
+    np.testing.assert_allclose(li["loss"], info["loss"], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(li["constraint_val"], info["constraint_val"], rtol=1e-6)
+    x_dev = algo.optimizer._bufs["x"].cpu().numpy()
+    assert _rel(x_dev, info["descent_direction"]) < 1e-6
