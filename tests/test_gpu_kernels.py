@@ -438,3 +438,32 @@ def test_step_size_axpy_adam_match_oracle(dev):
         ops.adam_step(td, out32, torch.tensor(g, dtype=torch.float64, device=dev), m, v, t)
         th_o, m_o, v_o, t_o = P.adam_step(th_o, g, m_o, v_o, t_o)
     np.testing.assert_allclose(td.cpu().numpy(), th_o, rtol=1e-12)
+
+
+@pytest.mark.parametrize("env_name,hidden", [("cartpole", 32), ("point", 32), ("cartpole", 64)])
+def test_f64_parity_kernels_match_oracle(dev, env_name, hidden):
+    """b200rl_update_f64 (float64 arithmetic on the float64 master parameters) vs the float64 oracle: 1e-9."""
+    L = _L()
+    ops, env, dims, theta, b, batch = _update_setup(dev, env_name, hidden)
+    dd = (env.O, hidden, hidden, env.A)
+    B = b.B
+    rng = np.random.RandomState(4)
+    th = theta + rng.randn(dims.P) * 0.02                     # NOT rounded to float32
+    thd = torch.tensor(th, dtype=torch.float64, device=dev)
+    out = torch.zeros(3, dtype=torch.float64, device=dev)
+    g = torch.zeros(dims.P, dtype=torch.float64, device=dev)
+    for kind, name in ((L.LOSS_TRPO, "trpo"), (L.LOSS_VPG, "vpg")):
+        ops.update_f64(0, kind, thd, dd, 1e-6, b, None, 1.0 / B, 0.0, 0.0, None, out)
+        ref_loss = P.surr_loss_trpo(th, batch, dims) if name == "trpo" else P.surr_loss_vpg(th, batch, dims)
+        mkl, xkl = P.kl_stats(th, batch, dims)
+        np.testing.assert_allclose(out.cpu().numpy(), [ref_loss, mkl, xkl], rtol=1e-9, atol=1e-13)
+        ops.update_f64(1, kind, thd, dd, 1e-6, b, None, 1.0 / B, 0.0, 0.0, g, out)
+        ref_g = P.grad_surr(th, batch, dims, name)
+        np.testing.assert_allclose(g.cpu().numpy(), ref_g, rtol=1e-8, atol=1e-12 * np.abs(ref_g).max())
+    x = rng.randn(dims.P)
+    xd = torch.tensor(x, dtype=torch.float64, device=dev)
+    Hx = torch.zeros(dims.P, dtype=torch.float64, device=dev)
+    th0 = torch.tensor(theta, dtype=torch.float64, device=dev)
+    ops.update_f64(2, L.LOSS_TRPO, th0, dd, 1e-6, b, xd, 1.0 / B, 1e-5, 1.0, Hx, None)
+    ref_Hx = P.fvp(theta, batch, x, dims, 1e-5)
+    np.testing.assert_allclose(Hx.cpu().numpy(), ref_Hx, rtol=1e-8, atol=1e-12 * np.abs(ref_Hx).max())
