@@ -30,32 +30,43 @@ int num_sms() {
   return sms;
 }
 
-__global__ void finalize_sum_kernel(const double* __restrict__ partial, int nblocks, int K, double* __restrict__ out,
-                                    double scale) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * K + k];
-  out[k] = s * scale;
-}
-
-__global__ void finalize_max_kernel(const double* __restrict__ partial, int nblocks, int K, double* __restrict__ out) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
-  double s = -1.0e300;
-  for (int b = 0; b < nblocks; ++b) s = fmax(s, partial[(size_t)b * K + k]);
-  out[k] = s;
+// out[k] = op over blocks of partial[b][k].  32 outputs x 8 block-slices per CTA: each slice walks every 8th block
+// (coalesced 256 B rows, 4 loads in flight), the slices are combined through shared memory in fixed order, so the result
+// is deterministic and the dependent-add chain is nblocks/8 long instead of nblocks (the one-thread-per-output version
+// cost ~56 us per call, 4 % of the cfg2 iteration -- profiles/r01c).
+template <bool IS_MAX>
+__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partial, int nblocks, int K,
+                                                       double* __restrict__ out, double scale) {
+  __shared__ double sm[8][33];
+  const int kx = threadIdx.x & 31, by = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + kx;
+  double acc = IS_MAX ? -1.0e300 : 0.0;
+  if (k < K) {
+#pragma unroll 4
+    for (int b = by; b < nblocks; b += 8) {
+      const double v = partial[(size_t)b * K + k];
+      acc = IS_MAX ? fmax(acc, v) : acc + v;
+    }
+  }
+  sm[by][kx] = acc;
+  __syncthreads();
+  if (by == 0 && k < K) {
+    double r = sm[0][kx];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) r = IS_MAX ? fmax(r, sm[y][kx]) : r + sm[y][kx];
+    out[k] = IS_MAX ? r : r * scale;
+  }
 }
 
 int launch_finalize_sum(const double* partial, int nblocks, int K, double* out, double scale, cudaStream_t s) {
-  finalize_sum_kernel<<<(K + 127) / 128, 128, 0, s>>>(partial, nblocks, K, out, scale);
-  B200RL_LAUNCH_CHECK("finalize_sum_kernel");
+  finalize_kernel<false><<<(K + 31) / 32, 256, 0, s>>>(partial, nblocks, K, out, scale);
+  B200RL_LAUNCH_CHECK("finalize_kernel<sum>");
   return 0;
 }
 
 int launch_finalize_max(const double* partial, int nblocks, int K, double* out, cudaStream_t s) {
-  finalize_max_kernel<<<(K + 127) / 128, 128, 0, s>>>(partial, nblocks, K, out);
-  B200RL_LAUNCH_CHECK("finalize_max_kernel");
+  finalize_kernel<true><<<(K + 31) / 32, 256, 0, s>>>(partial, nblocks, K, out, 1.0);
+  B200RL_LAUNCH_CHECK("finalize_kernel<max>");
   return 0;
 }
 

@@ -313,7 +313,7 @@ int b200rl_lfb_gram(int obs_dim, long long B, const float* obs, const unsigned s
   const size_t smem = (size_t)d1 * GRAM_LD * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (obs_dim <= 4) {
-    long long g = (long long)num_sms() * 8;
+    long long g = (long long)num_sms() * 4;   // 2 resident CTAs (233 registers) x 2 waves
     const long long need = (B + 127) / 128;
     if (g > need) g = need;
     grid = (int)g;
