@@ -96,7 +96,7 @@ struct PlanarKin {
 
 // d(r) = d0 + (d1-d0) min(|r|/width, 1)
 __device__ __forceinline__ float planar_imp(float d0, float d1, float w, float r) {
-  return d0 + (d1 - d0) * fminf(fabsf(r) / w, 1.0f);
+  return d0 + (d1 - d0) * fminf(fabsf(r) * (1.0f / w), 1.0f);
 }
 
 // qacc, qfrc_constraint and COM quantities at (q, v, ctrl).
@@ -179,7 +179,7 @@ __device__ __forceinline__ void planar_dynamics(const float (&q)[M::nv], const f
     (void)rox;
     cvX += cp.m * (hdx[i] - om[i] * roy);
   }
-  kin.comX = comX / mt; kin.comY = comY / mt; kin.comvelX = cvX / mt;
+  { const float imt = 1.0f / mt; kin.comX = comX * imt; kin.comY = comY * imt; kin.comvelX = cvX * imt; }
 #pragma unroll
   for (int r = 0; r < nv; ++r) {
     Mm[r][r] += M::armature(r);
@@ -188,6 +188,7 @@ __device__ __forceinline__ void planar_dynamics(const float (&q)[M::nv], const f
 #pragma unroll
   for (int j = 0; j < M::nu; ++j) tau[2 + M::act(j)] += fminf(fmaxf(ctrl[j], -M::ctrl_lim), M::ctrl_lim);
   // ---- Cholesky (lower factor stored in the lower triangle of Mm)
+  float idg[nv];
 #pragma unroll
   for (int r = 0; r < nv; ++r) {
 #pragma unroll
@@ -195,8 +196,10 @@ __device__ __forceinline__ void planar_dynamics(const float (&q)[M::nv], const f
       float s = Mm[c][r];  // upper entry (c <= r)
 #pragma unroll
       for (int k = 0; k < c; ++k) s -= Mm[r][k] * Mm[c][k];
-      if (c == r) Mm[r][r] = sqrtf(s);
-      else Mm[r][c] = s / Mm[c][c];
+      // reciprocal diagonal (MUFU.RSQ) kept in idg[]: every later division by L[r][r] becomes a multiply -- an IEEE
+      // float division is ~10 instructions + a slow-path CALL, and the Cholesky / triangular solves had ~40 of them per call
+      if (c == r) { idg[r] = rsqrtf(s); Mm[r][r] = s * idg[r]; }
+      else Mm[r][c] = s * idg[c];
     }
   }
   auto solve = [&](const float (&b)[nv], float (&x)[nv]) {
@@ -206,14 +209,14 @@ __device__ __forceinline__ void planar_dynamics(const float (&q)[M::nv], const f
       float s = b[r];
 #pragma unroll
       for (int k = 0; k < r; ++k) s -= Mm[r][k] * y[k];
-      y[r] = s / Mm[r][r];
+      y[r] = s * idg[r];
     }
 #pragma unroll
     for (int r = nv - 1; r >= 0; --r) {
       float s = y[r];
 #pragma unroll
       for (int k = r + 1; k < nv; ++k) s -= Mm[k][r] * x[k];
-      x[r] = s / Mm[r][r];
+      x[r] = s * idg[r];
     }
   };
   float a0[nv];
@@ -281,7 +284,7 @@ __device__ __forceinline__ void planar_dynamics(const float (&q)[M::nv], const f
     for (int k = 0; k < nv; ++k) acc[k] = a0[k];
     return;
   }
-  float MiJ[NC][nv], A[NC][NC], rhs[NC], Rr[NC], f[NC];
+  float MiJ[NC][nv], A[NC][NC], rhs[NC], Rr[NC], f[NC], iden[NC];
 #pragma unroll
   for (int i = 0; i < NC; ++i) solve(J[i], MiJ[i]);
 #pragma unroll
@@ -298,6 +301,7 @@ __device__ __forceinline__ void planar_dynamics(const float (&q)[M::nv], const f
       A[i][j] = t;
     }
     Rr[i] = (1.0f - dimp[i]) / dimp[i] * A[i][i];
+    iden[i] = 1.0f / (A[i][i] + Rr[i]);   // hoisted out of the PGS sweeps
     f[i] = 0.f;
   }
   for (int sweep = 0; sweep < PLANAR_PGS_SWEEPS; ++sweep) {
@@ -306,7 +310,7 @@ __device__ __forceinline__ void planar_dynamics(const float (&q)[M::nv], const f
       float s = rhs[i] - Rr[i] * f[i];
 #pragma unroll
       for (int j = 0; j < NC; ++j) s -= A[i][j] * f[j];
-      float fi = f[i] + s / (A[i][i] + Rr[i]);
+      float fi = f[i] + s * iden[i];
       const bool tangential = (i >= M::nlim) && (((i - M::nlim) & 1) == 1);
       if (!tangential) fi = fmaxf(fi, 0.f);
       else {
@@ -358,7 +362,7 @@ __device__ __forceinline__ void planar_kin(const float (&q)[M::nv], const float 
     mt += cp.m; comX += cp.m * (hx + rcx); comY += cp.m * (hy + rcy);
     cvX += cp.m * (hdx - om[i] * roy);
   }
-  kin.comX = comX / mt; kin.comY = comY / mt; kin.comvelX = cvX / mt;
+  { const float imt = 1.0f / mt; kin.comX = comX * imt; kin.comY = comY * imt; kin.comvelX = cvX * imt; }
 }
 
 // frame_skip x (semi-implicit Euler | RK4).  RK4 is written as a 4-stage loop so that the (inlined) dynamics has a
