@@ -94,6 +94,16 @@ struct PlanarKin {
   float comX, comY, comvelX;
 };
 
+// sin/cos of a body angle: two-constant Cody-Waite reduction to [-pi, pi] + MUFU.SIN/COS (abs. error ~5e-7).  The
+// library sincosf carries a Payne-Hanek slow path (CALL + convergence barrier at each of the 13 call sites) that the
+// bounded joint angles never need; together with the IEEE divisions it made up most of the integrator's latency.
+__device__ __forceinline__ void planar_sincos(float x, float* s, float* c) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, x);
+  r = fmaf(k, 1.7484555e-7f, r);
+  __sincosf(r, s, c);
+}
+
 // d(r) = d0 + (d1-d0) min(|r|/width, 1)
 __device__ __forceinline__ float planar_imp(float d0, float d1, float w, float r) {
   return d0 + (d1 - d0) * fminf(fabsf(r) * (1.0f / w), 1.0f);
@@ -113,7 +123,7 @@ __device__ __forceinline__ void planar_dynamics(const float (&q)[M::nv], const f
       ap += M::sgn(i) * q[2 + i];
       aw += M::sgn(i) * v[2 + i];
       om[i] = aw;
-      sincosf(ap, &sn[i], &cs[i]);
+      planar_sincos(ap, &sn[i], &cs[i]);
     }
   }
   float hx[n], hy[n], hdx[n], hdy[n], hddx[n], hddy[n];
@@ -344,7 +354,7 @@ __device__ __forceinline__ void planar_kin(const float (&q)[M::nv], const float 
       ap += M::sgn(i) * q[2 + i];
       aw += M::sgn(i) * v[2 + i];
       om[i] = aw;
-      sincosf(ap, &sn[i], &cs[i]);
+      planar_sincos(ap, &sn[i], &cs[i]);
     }
   }
   float hx = q[M::iX], hy = q[M::iY], hdx = v[M::iX], hdy = v[M::iY];
