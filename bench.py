@@ -162,8 +162,10 @@ def main():
                     value=value, unit="env-steps/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic", impl="reference",
-                    config=dict(workload=args.workload, env=env_name, algo=algo_name, hidden=[hidden, hidden],
-                                horizon=T, note="bounded sample on host cores"),
+                    config=dict(workload=args.workload, env=env_name, algo=algo_name, lanes_per_gpu=lanes, horizon=T,
+                                hidden=[hidden, hidden], samples_per_step=lanes * T * args.gpus,
+                                parallelism="host process pool (%d workers)" % info["cores"],
+                                note="each step is a bounded sample of the workload (see cpu_baseline.sample)"),
                     cpu_baseline=info,
                     e2e=dict(value=value, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     gpu_launches=0)
