@@ -71,8 +71,11 @@ struct Philox {
 
 // counter = (lane, row | stream<<28, chunk, lane>>32), key = (seed, iter).  Four floats per call.
 // uniform: (x>>8) * 2^-24 in [0,1);  normal: Box-Muller on ((x>>8)+0.5)*2^-24 in (0,1).
-__device__ inline void noise4(int kind, uint32_t seed, uint32_t iter, int stream_id, long long lane, int row,
-                              int chunk, float out[4]) {
+// NPAIRS: how many of the two Box-Muller pairs are needed (action noise of a 1- or 2-dimensional action space only
+// consumes the first pair: half the log / sqrt / sincospi work of the hot loop).
+template <int NPAIRS = 2>
+__device__ __forceinline__ void noise4(int kind, uint32_t seed, uint32_t iter, int stream_id, long long lane, int row,
+                                       int chunk, float out[4]) {
   uint32_t r[4];
   Philox::gen((uint32_t)lane, (uint32_t)row | ((uint32_t)stream_id << 28), (uint32_t)chunk,
               (uint32_t)((unsigned long long)lane >> 32), seed, iter, r);
@@ -82,10 +85,11 @@ __device__ inline void noise4(int kind, uint32_t seed, uint32_t iter, int stream
     for (int i = 0; i < 4; ++i) out[i] = (float)(r[i] >> 8) * s;
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; i += 2) {
-      float u1 = ((float)(r[i] >> 8) + 0.5f) * s;
-      float u2 = ((float)(r[i + 1] >> 8) + 0.5f) * s;
-      float rad = sqrtf(-2.0f * logf(u1));
+    for (int i = 0; i < 2 * NPAIRS; i += 2) {
+      const float u1 = ((float)(r[i] >> 8) + 0.5f) * s;          // in (0, 1): -2 log u1 > 0
+      const float u2 = ((float)(r[i + 1] >> 8) + 0.5f) * s;
+      const float t = -2.0f * logf(u1);
+      const float rad = t * rsqrtf(t);                            // sqrt without the IEEE slow path (t >= 6e-8)
       float sn, cs;
       sincospif(2.0f * u2, &sn, &cs);
       out[i] = rad * cs;

@@ -44,7 +44,7 @@ __device__ __forceinline__ void draw_eps(float (&e)[A], const float* __restrict_
     for (int a = 0; a < A; ++a) e[a] = eps[((size_t)row * A + a) * N + n];
   } else {
     float q[4];
-    noise4(B200RL_NOISE_NORMAL, seed, iter, 0, lane, row, 0, q);
+    noise4<(A + 1) / 2>(B200RL_NOISE_NORMAL, seed, iter, 0, lane, row, 0, q);
 #pragma unroll
     for (int a = 0; a < A; ++a) e[a] = q[a];
   }
