@@ -86,10 +86,11 @@ __device__ __forceinline__ void noise4(int kind, uint32_t seed, uint32_t iter, i
   } else {
 #pragma unroll
     for (int i = 0; i < 2 * NPAIRS; i += 2) {
-      const float u1 = ((float)(r[i] >> 8) + 0.5f) * s;          // in (0, 1): -2 log u1 > 0
+      const float u1 = ((float)(r[i] >> 8) + 0.5f) * s;          // in (0, 1]: 16777215.5 rounds up to 2^24 in float32
       const float u2 = ((float)(r[i + 1] >> 8) + 0.5f) * s;
-      const float t = -2.0f * logf(u1);
-      const float rad = t * rsqrtf(t);                            // sqrt without the IEEE slow path (t >= 6e-8)
+      // IEEE sqrtf on purpose: u1 == 1 gives t == 0 and t * rsqrtf(t) would be 0 * inf = NaN (one sample in 2^24 --
+      // caught by tests/test_gpu_fullsize.py on the 13.1 M-sample batch)
+      const float rad = sqrtf(-2.0f * logf(u1));
       float sn, cs;
       sincospif(2.0f * u2, &sn, &cs);
       out[i] = rad * cs;

@@ -43,7 +43,8 @@ def test_rollout_bookkeeping_invariants(full):
     assert bool((ts[1:] == nxt).all())                           # tstep restarts after every path end, else +1
     assert int((ts == 0).sum()) == int(end.sum())                # one start per end: every sample in exactly one path
     assert int(ts.max()) < MPL
-    assert bool(torch.isfinite(b.obs).all()) and bool(torch.isfinite(b.rew).all())
+    for k in ("obs", "act", "mean", "rew"):
+        assert bool(torch.isfinite(getattr(b, k)).all()), k
     # CartPole: a non-terminal step pays ~10, a terminal one 0 (cartpole_env.py:46-51)
     assert bool((b.rew[done] == 0).all()) and bool((b.rew[~done] > 9.0).all())
 
