@@ -133,6 +133,12 @@ int b200rl_center_advantages(float* adv, long long B, const double* sums, const 
 int b200rl_lfb_gram(int obs_dim, long long B, const float* obs, const unsigned short* tstep, const float* ret,
                     double* gram_out, double* ws, void* stream);
 
+/* The d x d solve of LinearFeatureBaseline.fit on the device (linear_feature_baseline.py:26-37): w_out [d = 2O+4]
+ * float64 from gram (b200rl_lfb_gram layout, already all-reduced), regularisation reg_coeff escalated x10 up to 5 times
+ * while the Cholesky solve fails; info_out [3] = (final reg, attempts used, ok flag).  Keeps the baseline fit free of
+ * host round trips. */
+int b200rl_lfb_solve(int obs_dim, const double* gram, double reg_coeff, double* w_out, double* info_out, void* stream);
+
 /* Surrogate loss and KL(old||new) (npo.py:72-82, vpg.py:91-99, diagonal_gaussian.py:14-34,58-69):
  * out[0] = scale * sum(-w*adv) (w = likelihood ratio for TRPO, logp for VPG), out[1] = scale * sum(kl),
  * out[2] = max(kl).  old_log_std [A] (state-independent ParamLayer, lasagne_layers.py:9-30). */

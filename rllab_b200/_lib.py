@@ -41,6 +41,7 @@ SIGNATURES = {
                                        _P, _P]),
     "b200rl_center_advantages": (c_int, [_P, _LL, _P, _P, c_int, c_int, _P]),
     "b200rl_lfb_gram": (c_int, [c_int, _LL, _P, _P, _P, _P, _P, _P]),
+    "b200rl_lfb_solve": (c_int, [c_int, _P, c_double, _P, _P, _P]),
     "b200rl_loss_kl": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, _P, _P, _P, c_double, _P,
                                _P, _P]),
     "b200rl_grad": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, _P, _P, _P, c_double, _P, _P,

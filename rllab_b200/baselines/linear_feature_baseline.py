@@ -2,9 +2,10 @@
 
 Host API (fit(paths) / predict(path) on the reference's path dicts) is kept verbatim for callers that hold host
 paths.  The hot path uses the device hooks: `device_weights` feeds b200rl_process_samples (predict), and `fit_lanes`
-reduces the normal equations A^T A | A^T y with b200rl_lfb_gram (one all-reduce across GPUs) and solves the d x d
-system (d = 2*obs_dim+4 <= 44) with the same np.linalg.lstsq + 10x-regularisation retry loop as the reference
-(:26-37)."""
+reduces the normal equations A^T A | A^T y with b200rl_lfb_gram (one all-reduce across GPUs) and solves the
+regularised d x d system (d = 2*obs_dim+4 <= 44) on the device with b200rl_lfb_solve, including the reference's
+10x-regularisation retry loop (:26-37) -- no host round trip; the coefficients are copied to the host only when
+get_param_values() / predict(path) / pickling asks for them."""
 import numpy as np
 
 
@@ -13,9 +14,6 @@ class LinearFeatureBaseline(object):
         self._coeffs = None
         self._reg_coeff = reg_coeff
         self._dev_w = None
-
-    def get_param_values(self, **tags):
-        return self._coeffs
 
     def set_param_values(self, val, **tags):
         self._coeffs = val
@@ -42,16 +40,22 @@ class LinearFeatureBaseline(object):
         self._solve(featmat.T.dot(featmat), featmat.T.dot(returns))
 
     def predict(self, path):
-        if self._coeffs is None:
+        coeffs = self.get_param_values()
+        if coeffs is None:
             return np.zeros(len(path["rewards"]))
-        return self._features(path).dot(self._coeffs)
+        return self._features(path).dot(coeffs)
 
     def log_diagnostics(self, paths):
         pass
 
-    # ---- device hooks
+    # ---- device hooks (no host round trip: Gram reduction, all-reduce and the d x d Cholesky solve stay on the GPU)
+    def get_param_values(self, **tags):
+        if self._coeffs is None and self._dev_w is not None:
+            self._coeffs = self._dev_w.cpu().numpy()
+        return self._coeffs
+
     def device_weights(self, obs_dim, device):
-        if self._coeffs is None:
+        if self._dev_w is None and self._coeffs is None:
             return None
         if self._dev_w is None or self._dev_w.device != device:
             import torch
@@ -63,11 +67,20 @@ class LinearFeatureBaseline(object):
         import torch
         from .. import ops
         d1 = 2 * batch.O + 5
-        gram = torch.empty((d1 * (d1 + 1) // 2,), dtype=torch.float64, device=batch.device)
-        ops.lfb_gram(batch, gram)
+        if getattr(self, "_gram", None) is None or self._gram.device != batch.device or self._gram.numel() != d1 * (d1 + 1) // 2:
+            self._gram = torch.empty((d1 * (d1 + 1) // 2,), dtype=torch.float64, device=batch.device)
+            self._w_next = torch.empty((d1 - 1,), dtype=torch.float64, device=batch.device)
+            self._solve_info = torch.zeros((3,), dtype=torch.float64, device=batch.device)
+        ops.lfb_gram(batch, self._gram)
         if comm is not None:
-            comm.all_reduce_sum(gram)
-        G = np.zeros((d1, d1))
-        G[np.triu_indices(d1)] = gram.cpu().numpy()
-        G = G + G.T - np.diag(np.diag(G))
-        self._solve(G[:-1, :-1], G[:-1, -1])
+            comm.all_reduce_sum(self._gram)
+        ops.lfb_solve(batch.O, self._gram, self._reg_coeff, self._w_next, self._solve_info)
+        self._dev_w = self._w_next.clone()
+        self._coeffs = None            # fetched lazily by get_param_values()
+
+    def __getstate__(self):
+        return dict(_coeffs=self.get_param_values(), _reg_coeff=self._reg_coeff)
+
+    def __setstate__(self, d):
+        self._coeffs, self._reg_coeff = d["_coeffs"], d["_reg_coeff"]
+        self._dev_w = None

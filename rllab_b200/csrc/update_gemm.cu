@@ -21,7 +21,7 @@
 
 namespace b200rl {
 
-constexpr int G_THREADS = 128, G_TS = 128, G_LD = G_TS + 4, G_FLUSH = 8;
+constexpr int G_TS = 128, G_LD = G_TS + 4, G_FLUSH = 8;   // 128 or 256 threads per 128-sample tile (template NTH)
 
 template <class N, int MODE>
 struct GemmSmem {
@@ -140,10 +140,14 @@ __device__ __forceinline__ void store_scaled_tile(const float2 (&ae)[4][RJ], con
   }
 }
 
-template <class N, int MODE>
-__global__ void __launch_bounds__(G_THREADS, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel(UpdArgs a) {
+// NTH = 128: register tile 8 samples x H/8 units; NTH = 256 (64-wide nets): 8 samples x H/16 units, two warps per
+// scheduler so that shared-memory latency overlaps with the FFMA2 chains of the other warp.
+template <class N, int MODE, int NTH>
+__global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel(UpdArgs a) {
   using SM = GemmSmem<N, MODE>;
-  constexpr int O = N::O, H = N::H1, A = N::A, P = N::P, LD = G_LD, RJ = H / 8;
+  constexpr int G_THREADS = NTH, UG = NTH / 16;          // unit groups per 8-sample group
+  constexpr int O = N::O, H = N::H1, A = N::A, P = N::P, LD = G_LD, RJ = H / UG;
+  static_assert(RJ % 4 == 0 && RJ >= 4, "register tile width must be a multiple of 4 units");
   constexpr int NT1 = (H / 4) * (H / 4);                 // 4x4 Gram tiles of dW1
   constexpr int KSPLIT = (NT1 <= 64) ? 2 : 1;            // H=32: 64 tiles x 2 K-halves; H=64: 256 tiles, 2 per thread
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(G_THREADS, (N::H1 == 32 ? 2 : 1)) update_gemm_
   D.half_log2pi_A = 0.5f * (float)A * 1.8378770664093453f;
 
   // GEMM tile ownership: 16 sample groups of 8 x 8 unit groups of RJ
-  const int og = tid & 7, sg = tid >> 3;
+  const int og = tid % UG, sg = tid / UG;
   const int s0 = sg * 8, j0 = og * RJ;
   // Gram ownership
   constexpr int GT = (KSPLIT == 2) ? 1 : NT1 / G_THREADS;   // 4x4 tiles per thread
@@ -264,12 +268,15 @@ __global__ void __launch_bounds__(G_THREADS, (N::H1 == 32 ? 2 : 1)) update_gemm_
   int since_flush = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     asm volatile("" ::: "memory");
+    const bool own_sample = (NTH == G_TS) || tid < G_TS;      // "thread = sample" phases (S0, S3)
     const long long s = tile * G_TS + tid;
-    const bool valid = s < a.B;
-    const long long sl = valid ? s : a.B - 1;
+    const bool valid = own_sample && s < a.B;
+    const long long sl = (s < a.B) ? s : a.B - 1;
     // ---- S0: observations
+    if (own_sample) {
 #pragma unroll
-    for (int o = 0; o < O; ++o) stage[(SM::rX + o) * LD + tid] = a.obs[(size_t)o * a.B + sl];
+      for (int o = 0; o < O; ++o) stage[(SM::rX + o) * LD + tid] = a.obs[(size_t)o * a.B + sl];
+    }
     __syncthreads();
     // ---- S1: H1 = tanh(W0^T X + b0)   (and, FVP, T1 = (1-H1^2)(V0^T X + vb0) -> D1 rows)
     {
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(G_THREADS, (N::H1 == 32 ? 2 : 1)) update_gemm_
     }
     __syncthreads();
     // ---- S3: per-sample distribution math (thread = sample)
-    {
+    if (own_sample) {
       float dmu[A];
       if constexpr (MODE == MODE_GRAD) {
         float mu[A];
@@ -511,12 +518,13 @@ __global__ void __launch_bounds__(G_THREADS, (N::H1 == 32 ? 2 : 1)) update_gemm_
   }
 }
 
-template <class N, int MODE>
-static int launch_gemm(const UpdArgs& a, int* grid_out, cudaStream_t st) {
+template <class N, int MODE, int NTH>
+static int launch_gemm_nth(const UpdArgs& a, int* grid_out, cudaStream_t st) {
   using SM = GemmSmem<N, MODE>;
+  constexpr int G_THREADS = NTH;
   static bool attr_done = false;
   if (!attr_done) {
-    B200RL_CUDA_CHECK(cudaFuncSetAttribute(update_gemm_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200RL_CUDA_CHECK(cudaFuncSetAttribute(update_gemm_kernel<N, MODE, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)SM::bytes));
     attr_done = true;
   }
@@ -527,10 +535,29 @@ static int launch_gemm(const UpdArgs& a, int* grid_out, cudaStream_t st) {
   const long long ntiles = (a.B + G_TS - 1) / G_TS;
   if (grid > ntiles) grid = ntiles;
   if (grid > MAX_PARTIAL_BLOCKS) grid = MAX_PARTIAL_BLOCKS;
-  update_gemm_kernel<N, MODE><<<(unsigned)grid, G_THREADS, SM::bytes, st>>>(a);
+  update_gemm_kernel<N, MODE, NTH><<<(unsigned)grid, G_THREADS, SM::bytes, st>>>(a);
   B200RL_LAUNCH_CHECK("update_gemm_kernel");
   *grid_out = (int)grid;
   return 0;
+}
+
+// threads per tile: 128 for 32-wide nets; 64-wide nets: env B200RL_GEMM_THREADS = 128 | 256 (default 256: no
+// spills, two warps per scheduler -- Hopper FVP 4.7 -> 3.0 ms, grad 3.2 -> 2.4 ms)
+static int gemm_threads_64() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("B200RL_GEMM_THREADS");
+    cached = (e != nullptr && atoi(e) == 128) ? 128 : 256;
+  }
+  return cached;
+}
+
+template <class N, int MODE>
+static int launch_gemm(const UpdArgs& a, int* grid_out, cudaStream_t st) {
+  if constexpr (N::H1 == 64) {
+    if (gemm_threads_64() == 256) return launch_gemm_nth<N, MODE, 256>(a, grid_out, st);
+  }
+  return launch_gemm_nth<N, MODE, 128>(a, grid_out, st);
 }
 
 int update_gemm_launch(int mode, int obs_dim, int h, int act_dim, const UpdArgs& a, int* grid_out, int* P_out,

@@ -100,6 +100,71 @@ __global__ void adam_kernel(long long P, double* __restrict__ th, float* __restr
   th32[i] = (float)t;
 }
 
+// LinearFeatureBaseline.fit solve (linear_feature_baseline.py:26-37): (A^T A + reg I) w = A^T y from the packed upper
+// triangle of the (d+1)x(d+1) Gram matrix [features | returns]; float64 Cholesky by one block; like the reference, the
+// regularisation is multiplied by 10 (up to 5 attempts) while the solve fails (non-positive pivot / NaN).  The
+// reference calls np.linalg.lstsq on the same regularised normal equations; for this SPD system the two agree to
+// rounding.  d <= 44.
+constexpr int LFB_DMAX = 44;
+__global__ void __launch_bounds__(64) lfb_solve_kernel(const double* __restrict__ gram, int d, double reg0,
+                                                       double* __restrict__ w_out, double* __restrict__ info) {
+  __shared__ double A[LFB_DMAX][LFB_DMAX + 1];
+  __shared__ double bvec[LFB_DMAX], wv[LFB_DMAX];
+  __shared__ int ok;
+  const int d1 = d + 1, tid = threadIdx.x;
+  double reg = reg0;
+  int attempt = 0;
+  for (; attempt < 5; ++attempt) {
+    // unpack: packed index of (i, j), i <= j, row-major upper triangle of a d1 x d1 matrix
+    for (int e = tid; e < d * d; e += blockDim.x) {
+      const int i = e / d, j = e % d;
+      const int r = i < j ? i : j, c = i < j ? j : i;
+      const int p = r * d1 - r * (r - 1) / 2 + (c - r);
+      A[i][j] = gram[p] + (i == j ? reg : 0.0);
+    }
+    for (int i = tid; i < d; i += blockDim.x) bvec[i] = gram[i * d1 - i * (i - 1) / 2 + (d - i)];
+    if (tid == 0) ok = 1;
+    __syncthreads();
+    for (int k = 0; k < d; ++k) {
+      if (tid == 0) {
+        const double piv = A[k][k];
+        if (!(piv > 0.0)) ok = 0;
+        A[k][k] = sqrt(piv);
+      }
+      __syncthreads();
+      if (!ok) break;
+      const double lkk = A[k][k];
+      for (int i = k + 1 + tid; i < d; i += blockDim.x) A[i][k] /= lkk;
+      __syncthreads();
+      for (int i = k + 1 + tid; i < d; i += blockDim.x) {
+        const double lik = A[i][k];
+        for (int j = k + 1; j <= i; ++j) A[i][j] -= lik * A[j][k];
+      }
+      __syncthreads();
+    }
+    if (ok && tid == 0) {
+      for (int i = 0; i < d; ++i) {            // L y = b
+        double s = bvec[i];
+        for (int k = 0; k < i; ++k) s -= A[i][k] * wv[k];
+        wv[i] = s / A[i][i];
+      }
+      for (int i = d - 1; i >= 0; --i) {       // L^T w = y
+        double s = wv[i];
+        for (int k = i + 1; k < d; ++k) s -= A[k][i] * wv[k];
+        wv[i] = s / A[i][i];
+      }
+      for (int i = 0; i < d; ++i)
+        if (isnan(wv[i]) || isinf(wv[i])) ok = 0;
+    }
+    __syncthreads();
+    if (ok) break;
+    reg *= 10.0;
+    __syncthreads();
+  }
+  for (int i = tid; i < d; i += blockDim.x) w_out[i] = wv[i];
+  if (tid == 0) { info[0] = reg; info[1] = (double)attempt; info[2] = (double)ok; }
+}
+
 __global__ void f64_to_f32_kernel(long long n, const double* __restrict__ s, float* __restrict__ d) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = (float)s[i];
@@ -151,6 +216,13 @@ int b200rl_adam_step(long long P, double* theta, float* theta_f32, const double*
   adam_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, theta, theta_f32, g, m, v, a_t, b1,
                                                                               b2, eps);
   B200RL_LAUNCH_CHECK("adam_kernel");
+  return 0;
+}
+
+int b200rl_lfb_solve(int obs_dim, const double* gram, double reg_coeff, double* w_out, double* info_out, void* stream) {
+  B200RL_REQUIRE(gram && w_out && info_out && obs_dim > 0 && 2 * obs_dim + 4 <= LFB_DMAX, "lfb_solve: bad arguments");
+  lfb_solve_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(gram, 2 * obs_dim + 4, reg_coeff, w_out, info_out);
+  B200RL_LAUNCH_CHECK("lfb_solve_kernel");
   return 0;
 }
 

@@ -138,6 +138,11 @@ def lfb_gram(batch, gram_out):
            L.ptr(workspace(b.device)), _stream())
 
 
+def lfb_solve(obs_dim, gram, reg_coeff, w_out, info_out):
+    _chk(gram, F64, "gram"), _chk(w_out, F64, "w_out", 2 * obs_dim + 4), _chk(info_out, F64, "info_out", 3)
+    L.call("b200rl_lfb_solve", obs_dim, L.ptr(gram), float(reg_coeff), L.ptr(w_out), L.ptr(info_out), _stream())
+
+
 def loss_kl(loss_kind, params32, dims, min_std, batch, scale, out):
     O, h1, h2, A = dims
     b = batch

@@ -7,7 +7,7 @@ obtain_samples(itr)   one fused CUDA rollout of N lanes x T steps (b200rl_rollou
                       wire format (sampler/utils.py:37-43) on demand.
 process_samples(...)  baseline predict + GAE + returns + statistics (b200rl_process_samples), centering
                       (b200rl_center_advantages), then -- after the advantages, as base.py:163-167 -- the baseline
-                      fit (b200rl_lfb_gram + d x d solve); records the same tabular keys (base.py:170-180).
+                      fit (b200rl_lfb_gram + b200rl_lfb_solve); records the same tabular keys (base.py:170-180).
 
 Batch geometry: T = max_path_length steps per lane, N = ceil(batch_size / T) lanes in total (>= batch_size samples,
 whole paths, like the reference's threshold semantics stateful_pool.py:149-152), sharded contiguously over ranks.

@@ -282,6 +282,13 @@ def test_process_samples_matches_reference_golden(dev, golden):
         pred_dev = S.lfb_features_lanes(traj["obs"], traj["tstep"]).reshape(d1 - 1, -1).T @ fit
         pred_ref = S.lfb_features_lanes(traj["obs"], traj["tstep"]).reshape(d1 - 1, -1).T @ ref_fit
         np.testing.assert_allclose(pred_dev, pred_ref, rtol=2e-3, atol=2e-3)   # ill-conditioned d=10 on 161 samples
+        # ... and the product's device-side solve (b200rl_lfb_solve) against the reference's fit as well
+        w_dev = torch.empty((d1 - 1,), dtype=torch.float64, device=dev)
+        info = torch.zeros((3,), dtype=torch.float64, device=dev)
+        ops.lfb_solve(b.O, gram, 1e-5, w_dev, info)
+        assert info.cpu().tolist() == [1e-5, 0.0, 1.0]
+        pred_solve = S.lfb_features_lanes(traj["obs"], traj["tstep"]).reshape(d1 - 1, -1).T @ w_dev.cpu().numpy()
+        np.testing.assert_allclose(pred_solve, pred_ref, rtol=2e-3, atol=2e-3)
 
 
 @pytest.mark.parametrize("env_name", ["cartpole", "pendulum"])
@@ -310,6 +317,39 @@ def test_process_samples_matches_oracle_large(dev, env_name):
     F = np.concatenate([F, ref["ret"].reshape(1, -1)], axis=0)
     G = (F @ F.T)[np.triu_indices(d1)]
     np.testing.assert_allclose(gram.cpu().numpy(), G, rtol=2e-5, atol=1e-3)
+    # device solve == the reference's lstsq on the same regularised normal equations
+    w_dev = torch.empty((d1 - 1,), dtype=torch.float64, device=dev)
+    info = torch.zeros((3,), dtype=torch.float64, device=dev)
+    ops.lfb_solve(b.O, gram, 1e-5, w_dev, info)
+    Gf = np.zeros((d1, d1))
+    Gf[np.triu_indices(d1)] = gram.cpu().numpy()
+    Gf = Gf + Gf.T - np.diag(np.diag(Gf))
+    w_ref = S.lfb_fit_normal(Gf[:-1, :-1], Gf[:-1, -1])
+    Fm = F[:-1].T
+    np.testing.assert_allclose(Fm @ w_dev.cpu().numpy(), Fm @ w_ref, rtol=1e-6, atol=1e-6)
+    assert info.cpu().tolist()[1:] == [0.0, 1.0]
+
+
+def test_lfb_solve_regularisation_retry(dev):
+    """linear_feature_baseline.py:30-37: reg *= 10 while the solve fails; at most 5 attempts."""
+    ops = _ops()
+    O = 2
+    d1 = 2 * O + 5
+    rs = np.random.RandomState(3)
+    X = rs.randn(d1, 3)
+    G = X @ X.T - 2e-4 * np.eye(d1)       # rank 3 minus 2e-4 I: positive definite only once reg >= 1e-3 (3rd attempt)
+    gram = torch.tensor(G[np.triu_indices(d1)], dtype=torch.float64, device=dev)
+    w = torch.empty((d1 - 1,), dtype=torch.float64, device=dev)
+    info = torch.zeros((3,), dtype=torch.float64, device=dev)
+    ops.lfb_solve(O, gram, 1e-5, w, info)
+    reg, attempts, ok = info.cpu().tolist()
+    assert ok == 1.0 and attempts == 2.0 and abs(reg - 1e-3) < 1e-15
+    A = G[:-1, :-1] + reg * np.eye(d1 - 1)
+    np.testing.assert_allclose(A @ w.cpu().numpy(), G[:-1, -1], rtol=1e-6, atol=1e-6)
+    # a NaN Gram matrix exhausts the 5 attempts and reports failure
+    gram[3] = float("nan")
+    ops.lfb_solve(O, gram, 1e-5, w, info)
+    assert info.cpu().tolist()[1:] == [5.0, 0.0]
 
 
 # ------------------------------------------------------------------------------------------- update kernels
@@ -324,7 +364,8 @@ def _update_setup(dev, env_name, hidden, N=512, T=32):
     return ops, env, dims, theta, b, batch
 
 
-@pytest.mark.parametrize("env_name,hidden", [("cartpole", 32), ("point", 32), ("pendulum", 32), ("cartpole", 64)])
+@pytest.mark.parametrize("env_name,hidden", [("cartpole", 32), ("point", 32), ("pendulum", 32), ("cartpole", 64)] +
+                         ([("swimmer", 32), ("hopper", 64)] if "hopper" in ENVS else []))
 def test_loss_kl_grad_fvp_match_oracle(dev, env_name, hidden):
     L = _L()
     ops, env, dims, theta, b, batch = _update_setup(dev, env_name, hidden)
