@@ -228,7 +228,10 @@ def main():
     ms_dev = run(args.steps, itr, False)
     launches = (L.kernel_launches() - k0) / args.steps
     itr += args.steps
+    from rllab_b200 import ops
+    d2h0 = ops.PendingHost.bytes_total
     ms_e2e = run(args.steps, itr, True)
+    d2h_stats = (ops.PendingHost.bytes_total - d2h0) / args.steps    # statistics / loss triples read back per iteration
     itr += args.steps
     clk = clocks.stop() if clocks else None
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
@@ -294,7 +297,6 @@ def main():
         return
     value = steps_per_iter * args.steps / (ms_dev * 1e-3)
     e2e_value = steps_per_iter * args.steps / (ms_e2e * 1e-3)
-    d = 2 * O + 4
     P_ = policy.n_params
     line = dict(
         metric="env-steps/sec (full iteration: rollout + process_samples + %s update)" % algo_name.upper(),
@@ -305,7 +307,7 @@ def main():
                     hidden=[hidden, hidden], samples_per_step=steps_per_iter, parallelism="lanes sharded x%d" % world,
                     l2="trajectory buffers (%.0f MB/GPU) exceed the 126 MB L2" % (b.B * (alg_bytes + 14) / 1e6)),
         e2e=dict(value=e2e_value, unit="env-steps/s", ms_per_step=ms_e2e / args.steps,
-                 h2d_bytes_per_step=8 * P_ + 8 * d, d2h_bytes_per_step=8 * P_ + 8 * (16 + 4 + 3 * 3) + 8 * ((d + 1) * (d + 2) // 2)),
+                 h2d_bytes_per_step=8 * P_, d2h_bytes_per_step=8 * P_ + d2h_stats),
         gpu_launches=launches, clocks=clk, roofline=roofline,
         kernels={k: dict(ms=round(v["ms"], 4), GBps=round(v["GBps"], 1), per_iter=v["per_iter"],
                          share_of_step=round(v["share_of_step"], 3)) for k, v in kern.items()},

@@ -73,7 +73,9 @@ class BatchPolopt(RLAlgorithm):
         # log_std makes mean(exp(log_stds)) over samples equal to mean(exp(log_std)) over action dims.
         b = getattr(paths, "lane_batch", None)
         if b is not None:
-            logger.record_tabular('AveragePolicyStd', float(np.mean(np.exp(b.log_std.double().cpu().numpy()))))
+            from .. import ops
+            p_ls = ops.PendingHost(b.log_std)          # read back when the table is dumped
+            logger.record_tabular('AveragePolicyStd', lambda: float(np.mean(np.exp(p_ls.get().astype(np.float64)))))
             if self.store_paths:
                 self.env.log_diagnostics(paths.to_paths())
         else:

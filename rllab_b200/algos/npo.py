@@ -22,16 +22,15 @@ class NPO(BatchPolopt):
         return dict()
 
     def optimize_policy(self, itr, samples_data):
-        loss_before = self.optimizer.loss(samples_data)
-        mean_kl_before = self.optimizer.constraint_val(samples_data)
+        # npo.py:102-123; lazily read triples (see VPG.optimize_policy): the first host wait is at the line search
+        before = self.optimizer.eval_lazy(samples_data)
         self.optimizer.optimize(samples_data)
-        mean_kl = self.optimizer.constraint_val(samples_data)
-        loss_after = self.optimizer.loss(samples_data)
-        logger.record_tabular('LossBefore', loss_before)
-        logger.record_tabular('LossAfter', loss_after)
-        logger.record_tabular('MeanKLBefore', mean_kl_before)
-        logger.record_tabular('MeanKL', mean_kl)
-        logger.record_tabular('dLoss', loss_before - loss_after)
+        after = self.optimizer.eval_lazy(samples_data)
+        logger.record_tabular('LossBefore', lambda: before[0])
+        logger.record_tabular('LossAfter', lambda: after[0])
+        logger.record_tabular('MeanKLBefore', lambda: before[1])
+        logger.record_tabular('MeanKL', lambda: after[1])
+        logger.record_tabular('dLoss', lambda: before[0] - after[0])
         return dict()
 
     def get_itr_snapshot(self, itr, samples_data):

@@ -22,14 +22,15 @@ class VPG(BatchPolopt):
 
     def optimize_policy(self, itr, samples_data):
         logger.log("optimizing policy")
-        loss_before = self.optimizer.loss(samples_data)
+        # same quantities as vpg.py:110-130; the triples are read back lazily (resolved by logger.dump_tabular) so that
+        # the gradient pass, the Adam step and the evaluation pass are all queued before the host blocks
+        before = self.optimizer.eval_lazy(samples_data, want_grad=True)
         self.optimizer.optimize(samples_data)
-        loss_after = self.optimizer.loss(samples_data)
-        logger.record_tabular("LossBefore", loss_before)
-        logger.record_tabular("LossAfter", loss_after)
-        mean_kl, max_kl = self.opt_info['f_kl'](samples_data)
-        logger.record_tabular('MeanKL', mean_kl)
-        logger.record_tabular('MaxKL', max_kl)
+        after = self.optimizer.eval_lazy(samples_data)
+        logger.record_tabular("LossBefore", lambda: before[0])
+        logger.record_tabular("LossAfter", lambda: after[0])
+        logger.record_tabular('MeanKL', lambda: after[1])
+        logger.record_tabular('MaxKL', lambda: after[2])
 
     def get_itr_snapshot(self, itr, samples_data):
         return dict(itr=itr, policy=self.policy, baseline=self.baseline, env=self.env)

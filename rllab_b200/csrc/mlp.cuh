@@ -26,6 +26,19 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 #endif
 }
 
+// Gram products over the sample axis with packed FFMA2: four consecutive samples (one LDS.128 per row) are folded as two
+// (even, odd) pairs, so acc.x / acc.y are the even- / odd-sample partial sums and the caller adds the halves at the end.
+__device__ __forceinline__ void gram_fma4(const float4& u, const float4& v, float2& acc) {
+  acc = ffma2(make_float2(u.x, u.y), make_float2(v.x, v.y), acc);
+  acc = ffma2(make_float2(u.z, u.w), make_float2(v.z, v.w), acc);
+}
+__device__ __forceinline__ void gram_4x4(const float4 (&u)[4], const float4 (&v)[4], float2 (&acc)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) gram_fma4(u[r], v[c], acc[r][c]);
+}
+
 // Dense layer, thread-per-sample, weights W [NIN][NOUT] row-major + bias in shared memory (broadcast LDS.128).
 // Output pairs (j, j+1) share one packed FFMA2; even and odd inputs accumulate in separate chains (canonical order).
 // FENCE > 0 inserts a compiler memory barrier every FENCE input rows: it bounds how many weight loads ptxas may hoist

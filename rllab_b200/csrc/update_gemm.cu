@@ -192,17 +192,17 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
   const int s0 = sg * 8, j0 = og * RJ;
   // Gram ownership
   constexpr int GT = (KSPLIT == 2) ? 1 : NT1 / G_THREADS;   // 4x4 tiles per thread
-  float gW1[GT][4][4];
+  float2 gW1[GT][4][4];               // .x / .y: even- / odd-sample partial sums (packed FFMA2, see gram_fma4)
 #pragma unroll
   for (int g = 0; g < GT; ++g)
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) gW1[g][r][c] = 0.f;
+      for (int c = 0; c < 4; ++c) gW1[g][r][c] = make_float2(0.f, 0.f);
   constexpr int NS = (O + 2 > A + 1) ? O + 2 : A + 1;
-  float gS[NS];
+  float2 gS[NS];
 #pragma unroll
-  for (int k = 0; k < NS; ++k) gS[k] = 0.f;
+  for (int k = 0; k < NS; ++k) gS[k] = make_float2(0.f, 0.f);
   double s_loss = 0.0, s_kl = 0.0, m_kl = -1.0e300;
 
   auto flush = [&]() {
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) scr[w1_tile * 16 + r * 4 + c] = gW1[0][r][c];
+          for (int c = 0; c < 4; ++c) scr[w1_tile * 16 + r * 4 + c] = gW1[0][r][c].x + gW1[0][r][c].y;
       }
       __syncthreads();
       if (kh == 0) {
@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
         for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            out[N::oW1 + (ti + 8 * r) * H + (tj + 8 * c)] += (double)gW1[0][r][c] + (double)scr[w1_tile * 16 + r * 4 + c];
+            out[N::oW1 + (ti + 8 * r) * H + (tj + 8 * c)] +=
+                (double)(gW1[0][r][c].x + gW1[0][r][c].y) + (double)scr[w1_tile * 16 + r * 4 + c];
       }
     } else {
 #pragma unroll
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
         for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            out[N::oW1 + (ti + (H / 4) * r) * H + (tj + (H / 4) * c)] += (double)gW1[g][r][c];
+            out[N::oW1 + (ti + (H / 4) * r) * H + (tj + (H / 4) * c)] += (double)(gW1[g][r][c].x + gW1[g][r][c].y);
       }
     }
 #pragma unroll
@@ -242,25 +243,25 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) gW1[g][r][c] = 0.f;
+        for (int c = 0; c < 4; ++c) gW1[g][r][c] = make_float2(0.f, 0.f);
     // small outputs
     for (int task = tid; task < 2 * H; task += G_THREADS) {
       const int slot = task / G_THREADS;   // H=64: every thread has exactly one task; H=32: threads < 64
       (void)slot;
       if (task < H) {
 #pragma unroll
-        for (int o = 0; o < O; ++o) out[N::oW0 + o * H + task] += (double)gS[o];
-        out[N::ob0 + task] += (double)gS[O];
-        if (task < 2 * A) out[N::obo + task] += (double)gS[O + 1];   // bout[A] then log_std[A] are contiguous
+        for (int o = 0; o < O; ++o) out[N::oW0 + o * H + task] += (double)(gS[o].x + gS[o].y);
+        out[N::ob0 + task] += (double)(gS[O].x + gS[O].y);
+        if (task < 2 * A) out[N::obo + task] += (double)(gS[O + 1].x + gS[O + 1].y);   // bout[A], log_std[A] contiguous
       } else {
         const int j = task - H;
 #pragma unroll
-        for (int k = 0; k < A; ++k) out[N::oWo + j * A + k] += (double)gS[k];
-        out[N::ob1 + j] += (double)gS[A];
+        for (int k = 0; k < A; ++k) out[N::oWo + j * A + k] += (double)(gS[k].x + gS[k].y);
+        out[N::ob1 + j] += (double)(gS[A].x + gS[A].y);
       }
     }
 #pragma unroll
-    for (int k = 0; k < NS; ++k) gS[k] = 0.f;
+    for (int k = 0; k < NS; ++k) gS[k] = make_float2(0.f, 0.f);
     __syncthreads();
   };
 
@@ -431,13 +432,7 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
           for (int r = 0; r < 4; ++r) u[r] = *reinterpret_cast<const float4*>(U + r * 8 * LD + k);
 #pragma unroll
           for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(V + c * 8 * LD + k);
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              gW1[0][r][c] = fmaf(u[r].x, v[c].x, gW1[0][r][c]); gW1[0][r][c] = fmaf(u[r].y, v[c].y, gW1[0][r][c]);
-              gW1[0][r][c] = fmaf(u[r].z, v[c].z, gW1[0][r][c]); gW1[0][r][c] = fmaf(u[r].w, v[c].w, gW1[0][r][c]);
-            }
+          gram_4x4(u, v, gW1[0]);
         }
       } else {
 #pragma unroll
@@ -453,13 +448,7 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
             for (int r = 0; r < 4; ++r) u[r] = *reinterpret_cast<const float4*>(U + r * (H / 4) * LD + k);
 #pragma unroll
             for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(V + c * (H / 4) * LD + k);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                gW1[g][r][c] = fmaf(u[r].x, v[c].x, gW1[g][r][c]); gW1[g][r][c] = fmaf(u[r].y, v[c].y, gW1[g][r][c]);
-                gW1[g][r][c] = fmaf(u[r].z, v[c].z, gW1[g][r][c]); gW1[g][r][c] = fmaf(u[r].w, v[c].w, gW1[g][r][c]);
-              }
+            gram_4x4(u, v, gW1[g]);
           }
         }
       }
@@ -474,13 +463,12 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
 #pragma unroll
             for (int o = 0; o < O; ++o) {
               const float4 xv = *reinterpret_cast<const float4*>(stage + (SM::rX + o) * LD + k);
-              gS[o] = fmaf(xv.x, d.x, gS[o]); gS[o] = fmaf(xv.y, d.y, gS[o]);
-              gS[o] = fmaf(xv.z, d.z, gS[o]); gS[o] = fmaf(xv.w, d.w, gS[o]);
+              gram_fma4(xv, d, gS[o]);
             }
-            gS[O] += (d.x + d.y) + (d.z + d.w);
+            gS[O].x += (d.x + d.y) + (d.z + d.w);
             if (task < 2 * A) {
               const float4 e = *reinterpret_cast<const float4*>(Er + k);
-              gS[O + 1] += (e.x + e.y) + (e.z + e.w);
+              gS[O + 1].x += (e.x + e.y) + (e.z + e.w);
             }
           }
         } else {
@@ -494,10 +482,9 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
 #pragma unroll
             for (int q = 0; q < A; ++q) {
               const float4 m = *reinterpret_cast<const float4*>(stage + (SM::rDM + q) * LD + k);
-              gS[q] = fmaf(hv.x, m.x, gS[q]); gS[q] = fmaf(hv.y, m.y, gS[q]);
-              gS[q] = fmaf(hv.z, m.z, gS[q]); gS[q] = fmaf(hv.w, m.w, gS[q]);
+              gram_fma4(hv, m, gS[q]);
             }
-            gS[A] += (d.x + d.y) + (d.z + d.w);
+            gS[A].x += (d.x + d.y) + (d.z + d.w);
           }
         }
       }

@@ -42,6 +42,9 @@ def prefix(key):
 
 
 def record_tabular(key, val):
+    """val may be a zero-argument callable: it is resolved at dump_tabular().  The device hot path records its
+    statistics that way so that the device->host readback waits at the end of the iteration instead of idling the GPU
+    in the middle of it."""
     _tabular.append((str(key), val))
 
 
@@ -52,6 +55,7 @@ def get_last_table():
 
 def dump_tabular(*args, **kwargs):
     global _last_table
+    _tabular[:] = [(k, v() if callable(v) else v) for k, v in _tabular]
     _last_table = dict(_tabular)
     if not _quiet and len(_tabular) > 0:
         w = max(len(k) for k, _ in _tabular)

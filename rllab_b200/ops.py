@@ -210,3 +210,50 @@ def f64_to_f32(src, dst):
 def planes_to_rows_f64(src, dim, B, dst):
     _chk(src, F32, "src", dim * B), _chk(dst, F64, "dst", dim * B)
     L.call("b200rl_planes_to_rows_f64", dim, B, L.ptr(src), L.ptr(dst), _stream())
+
+
+class PendingHost(object):
+    """Asynchronous device->host readback of a small tensor: the copy into pinned host memory is queued on the current
+    stream together with an event; `get()` waits for that event only (not for later work on the stream) and returns a
+    numpy copy.  Lets an iteration queue all of its kernels before the host blocks once, at logging time.  Pinned
+    staging buffers are pooled (page-locking is far too slow to do per call)."""
+    _pool = {}
+    bytes_total = 0          # device->host bytes queued so far (bench.py reports the per-step figure)
+
+    def __init__(self, src):
+        import torch
+        PendingHost.bytes_total += src.numel() * src.element_size()
+        self._key = (tuple(src.shape), src.dtype)
+        free = PendingHost._pool.setdefault(self._key, [])
+        self._host = free.pop() if free else torch.empty(src.shape, dtype=src.dtype).pin_memory()
+        self._host.copy_(src, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+        self._val = None
+
+    def get(self):
+        if self._val is None:
+            self._event.synchronize()
+            self._val = self._host.numpy().copy()
+            PendingHost._pool[self._key].append(self._host)
+            self._host = None
+        return self._val
+
+
+class LazyTriple(object):
+    """(loss, mean KL, max KL) of one pass, read back lazily: indexing blocks on the readback event."""
+
+    def __init__(self, src):
+        self._p = PendingHost(src)
+        self._v = None
+
+    def values(self):
+        if self._v is None:
+            self._v = tuple(float(x) for x in self._p.get())
+        return self._v
+
+    def __getitem__(self, i):
+        return self.values()[i]
+
+    def __iter__(self):
+        return iter(self.values())

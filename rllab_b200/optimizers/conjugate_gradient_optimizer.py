@@ -98,9 +98,13 @@ class ConjugateGradientOptimizer(object):
         else:
             ops.loss_kl(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, b["out"])
         self._allreduce_out3(b["out"])
-        vals = tuple(float(v) for v in b["out"].cpu().numpy())
+        vals = ops.LazyTriple(b["out"])       # pinned-memory readback queued behind the pass; blocks when indexed
         self._cache = (key, vals)
         return vals
+
+    def eval_lazy(self, inputs, want_grad=True):
+        """The (loss, mean_kl, max_kl) triple as a lazily read ops.LazyTriple (see FirstOrderOptimizer.eval_lazy)."""
+        return self._eval(_lane_batch(inputs), want_grad=want_grad)
 
     def loss(self, inputs, extra_inputs=None):
         return self._eval(_lane_batch(inputs), want_grad=True)[0]
@@ -120,7 +124,7 @@ class ConjugateGradientOptimizer(object):
         ar = (lambda t: comm.all_reduce_sum(t)) if world > 1 else (lambda t: t)
 
         logger.log("computing loss before")
-        loss_before = self._eval(batch, want_grad=True)[0]
+        before = self._eval(batch, want_grad=True)      # read back at the line search, after the CG solve is queued
         logger.log("performing update")
         logger.log("computing descent direction")
         key0 = (pol.version, id(batch), batch.version)
@@ -154,6 +158,7 @@ class ConjugateGradientOptimizer(object):
         logger.log("descent direction computed")
 
         b["prev"].copy_(pol.theta64)
+        loss_before = before[0]
         n_iter = 0
         loss = constraint_val = np.nan
         for n_iter, ratio in enumerate(self._backtrack_ratio ** np.arange(self._max_backtracks)):

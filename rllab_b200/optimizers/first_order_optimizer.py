@@ -60,9 +60,14 @@ class FirstOrderOptimizer(object):
         if self._comm is not None and self._comm.active:
             self._comm.all_reduce_sum(self._out[:2])
             self._comm.all_reduce_max(self._out[2:])
-        vals = tuple(float(v) for v in self._out.cpu().numpy())
+        vals = ops.LazyTriple(self._out)      # pinned-memory readback queued behind the pass; blocks when indexed
         self._cache = (key, vals)
         return vals
+
+    def eval_lazy(self, inputs, want_grad=False):
+        """The (loss, mean_kl, max_kl) triple as a lazily read ops.LazyTriple: lets the caller queue the whole
+        iteration before the host blocks (the algos record `lambda: triple[0]` with the logger)."""
+        return self._eval(_lane_batch(inputs), want_grad=want_grad)
 
     def loss(self, inputs, extra_inputs=None):
         return self._eval(_lane_batch(inputs), want_grad=True)[0]
@@ -79,7 +84,7 @@ class FirstOrderOptimizer(object):
             raise NotImplementedError("mini-batch epochs are not on the B200 hot path (VPG uses batch_size=None)")
         pol = self._target
         self._state(batch.device)
-        last_loss = self._eval(batch, want_grad=True)[0]
+        last = self._eval(batch, want_grad=True)
         for epoch in range(self._max_epochs):
             if self._g_key != (pol.version, id(batch), batch.version):
                 ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, self._g)
@@ -89,16 +94,17 @@ class FirstOrderOptimizer(object):
             ops.adam_step(pol.theta64, pol.theta32, self._g, self._m, self._v, self._t, self._learning_rate, self._b1,
                           self._b2, self._eps)
             pol.bump_version()
-            new_loss = self._eval(batch)[0]
+            new = self._eval(batch)
             if self._callback or callback:
-                args = dict(loss=new_loss, params=pol.get_param_values(), itr=epoch, elapsed=0.0)
+                args = dict(loss=new[0], params=pol.get_param_values(), itr=epoch, elapsed=0.0)
                 if self._callback:
                     self._callback(args)
                 if callback:
                     callback(**args)
-            if abs(last_loss - new_loss) < self._tolerance:
-                break
-            last_loss = new_loss
+            if epoch + 1 < self._max_epochs:       # the tolerance test only matters if another epoch could follow;
+                if abs(last[0] - new[0]) < self._tolerance:   # with max_epochs=1 (VPG) nothing is read back here
+                    break
+                last = new
 
     def __getstate__(self):
         d = dict(self.__dict__)

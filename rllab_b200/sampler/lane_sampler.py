@@ -127,7 +127,8 @@ class LaneSampler(Sampler):
         self.seed = seed
         self.comm = comm
         self.batch = None
-        self.stats = {}
+        self._stats = None
+        self._pending = None
 
     def start_worker(self):
         import torch
@@ -189,8 +190,27 @@ class LaneSampler(Sampler):
         algo.baseline.fit_lanes(b, self.comm)
         logger.log("fitted")
 
-        s = b.sums.cpu().numpy()
-        m = b.maxs.cpu().numpy()
+        # statistics: queued pinned-memory readbacks, resolved when the logger dumps the table (or `stats` is read), so
+        # the host does not stall the GPU between process_samples and the policy update
+        self._pending = (itr, ops.PendingHost(b.sums), ops.PendingHost(b.maxs), ops.PendingHost(b.log_std))
+        self._stats = None
+        for k in ("Iteration", "AverageDiscountedReturn", "AverageReturn", "ExplainedVariance", "NumTrajs", "Entropy",
+                  "Perplexity", "StdReturn", "MaxReturn", "MinReturn"):
+            logger.record_tabular(k, lambda k=k: self.stats[k])
+        return samples_data
+
+    @property
+    def stats(self):
+        """The tabular statistics of the last process_samples (base.py:170-180), resolved on first use."""
+        if self._stats is None:
+            if self._pending is None:
+                return {}
+            self._stats = self._resolve_stats(*self._pending)
+        return self._stats
+
+    @staticmethod
+    def _resolve_stats(itr, p_sums, p_maxs, p_log_std):
+        s, m = p_sums.get(), p_maxs.get()
         n_paths = s[3]
         avg_ret = s[5] / n_paths
         vary = s[8] / s[2] - (s[7] / s[2]) ** 2
@@ -200,12 +220,8 @@ class LaneSampler(Sampler):
             ev = 0 if varpred > 0 else 1
         else:
             ev = 1 - varres / (vary + 1e-8)
-        ent = float(np.sum(b.log_std.double().cpu().numpy() + np.log(np.sqrt(2 * np.pi * np.e))))
-        self.stats = dict(
+        ent = float(np.sum(p_log_std.get().astype(np.float64) + np.log(np.sqrt(2 * np.pi * np.e))))
+        return dict(
             Iteration=itr, AverageDiscountedReturn=s[4] / n_paths, AverageReturn=avg_ret, ExplainedVariance=ev,
             NumTrajs=int(round(n_paths)), Entropy=ent, Perplexity=np.exp(ent),
             StdReturn=np.sqrt(max(s[6] / n_paths - avg_ret ** 2, 0.0)), MaxReturn=m[0], MinReturn=-m[1])
-        for k in ("Iteration", "AverageDiscountedReturn", "AverageReturn", "ExplainedVariance", "NumTrajs", "Entropy",
-                  "Perplexity", "StdReturn", "MaxReturn", "MinReturn"):
-            logger.record_tabular(k, self.stats[k])
-        return samples_data

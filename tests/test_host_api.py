@@ -102,6 +102,12 @@ def test_logger_tabular_and_snapshot(tmp_path):
         logger.record_tabular("NumTrajs", 7)
         logger.dump_tabular()
     assert logger.get_last_table() == {"AverageReturn": 1.5, "NumTrajs": 7}
+    # deferred values (device readbacks) are resolved when the table is dumped, not when they are recorded
+    box = {"v": 1.0}
+    logger.record_tabular("LossBefore", lambda: box["v"])
+    box["v"] = 2.0
+    logger.dump_tabular()
+    assert logger.get_last_table() == {"LossBefore": 2.0}
     logger.save_itr_params(0, dict(itr=0, x=np.arange(3)))
     d = pickle.load(open(str(tmp_path / "params.pkl"), "rb"))
     assert d["itr"] == 0
