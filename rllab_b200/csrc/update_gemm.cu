@@ -96,8 +96,19 @@ __device__ __forceinline__ void store_tanh_tile(const float2 (&ae)[4][RJ], const
   }
 }
 // activation cache <-> staged tile (RJ rows x 8 samples starting at sample index sbase; rows are B apart in the cache)
+// (rows of the cache are 16-byte aligned when B % 4 == 0: two LDG.128 / STG.128 per row instead of eight scalar accesses)
 template <int RJ>
 __device__ __forceinline__ void load_cached_tile(const float* src, long long B, long long sbase, float* dst) {
+  if ((B & 3) == 0 && sbase + 8 <= B) {
+#pragma unroll
+    for (int c = 0; c < RJ; ++c) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * B + sbase));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * B + sbase + 4));
+      *reinterpret_cast<float4*>(dst + c * G_LD) = v0;
+      *reinterpret_cast<float4*>(dst + c * G_LD + 4) = v1;
+    }
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < RJ; ++c) {
     float v[8];
@@ -112,6 +123,14 @@ __device__ __forceinline__ void load_cached_tile(const float* src, long long B, 
 }
 template <int RJ>
 __device__ __forceinline__ void save_cached_tile(const float* src, float* dst, long long B, long long sbase) {
+  if ((B & 3) == 0 && sbase + 8 <= B) {
+#pragma unroll
+    for (int c = 0; c < RJ; ++c) {
+      *reinterpret_cast<float4*>(dst + (size_t)c * B + sbase) = *reinterpret_cast<const float4*>(src + c * G_LD);
+      *reinterpret_cast<float4*>(dst + (size_t)c * B + sbase + 4) = *reinterpret_cast<const float4*>(src + c * G_LD + 4);
+    }
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < RJ; ++c) {
 #pragma unroll
@@ -219,23 +238,36 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
       }
       __syncthreads();
       if (kh == 0) {
+        // read-modify-write of this block's float64 partial: all loads first, then all stores (a chain of 16 dependent
+        // global round trips otherwise -- the compiler cannot reorder the loads across the stores)
+        double t[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) t[r][c] = out[N::oW1 + (ti + 8 * r) * H + (tj + 8 * c)];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            out[N::oW1 + (ti + 8 * r) * H + (tj + 8 * c)] +=
-                (double)(gW1[0][r][c].x + gW1[0][r][c].y) + (double)scr[w1_tile * 16 + r * 4 + c];
+            out[N::oW1 + (ti + 8 * r) * H + (tj + 8 * c)] =
+                t[r][c] + ((double)(gW1[0][r][c].x + gW1[0][r][c].y) + (double)scr[w1_tile * 16 + r * 4 + c]);
       }
     } else {
 #pragma unroll
       for (int g = 0; g < GT; ++g) {
         const int w1_tile = tid + g * G_THREADS;
         const int ti = w1_tile / (H / 4), tj = w1_tile % (H / 4);
+        double t[4][4];                        // loads first, then stores (see above)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) t[r][c] = out[N::oW1 + (ti + (H / 4) * r) * H + (tj + (H / 4) * c)];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            out[N::oW1 + (ti + (H / 4) * r) * H + (tj + (H / 4) * c)] += (double)(gW1[g][r][c].x + gW1[g][r][c].y);
+            out[N::oW1 + (ti + (H / 4) * r) * H + (tj + (H / 4) * c)] =
+                t[r][c] + (double)(gW1[g][r][c].x + gW1[g][r][c].y);
       }
     }
 #pragma unroll
@@ -249,15 +281,24 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
       const int slot = task / G_THREADS;   // H=64: every thread has exactly one task; H=32: threads < 64
       (void)slot;
       if (task < H) {
+        double t[O + 2];
 #pragma unroll
-        for (int o = 0; o < O; ++o) out[N::oW0 + o * H + task] += (double)(gS[o].x + gS[o].y);
-        out[N::ob0 + task] += (double)(gS[O].x + gS[O].y);
-        if (task < 2 * A) out[N::obo + task] += (double)(gS[O + 1].x + gS[O + 1].y);   // bout[A], log_std[A] contiguous
+        for (int o = 0; o < O; ++o) t[o] = out[N::oW0 + o * H + task];
+        t[O] = out[N::ob0 + task];
+        t[O + 1] = (task < 2 * A) ? out[N::obo + task] : 0.0;
+#pragma unroll
+        for (int o = 0; o < O; ++o) out[N::oW0 + o * H + task] = t[o] + (double)(gS[o].x + gS[o].y);
+        out[N::ob0 + task] = t[O] + (double)(gS[O].x + gS[O].y);
+        if (task < 2 * A) out[N::obo + task] = t[O + 1] + (double)(gS[O + 1].x + gS[O + 1].y);   // bout[A], log_std[A] contiguous
       } else {
         const int j = task - H;
+        double t[A + 1];
 #pragma unroll
-        for (int k = 0; k < A; ++k) out[N::oWo + j * A + k] += (double)(gS[k].x + gS[k].y);
-        out[N::ob1 + j] += (double)(gS[A].x + gS[A].y);
+        for (int k = 0; k < A; ++k) t[k] = out[N::oWo + j * A + k];
+        t[A] = out[N::ob1 + j];
+#pragma unroll
+        for (int k = 0; k < A; ++k) out[N::oWo + j * A + k] = t[k] + (double)(gS[k].x + gS[k].y);
+        out[N::ob1 + j] = t[A] + (double)(gS[A].x + gS[A].y);
       }
     }
 #pragma unroll
