@@ -278,8 +278,6 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
         for (int c = 0; c < 4; ++c) gW1[g][r][c] = make_float2(0.f, 0.f);
     // small outputs
     for (int task = tid; task < 2 * H; task += G_THREADS) {
-      const int slot = task / G_THREADS;   // H=64: every thread has exactly one task; H=32: threads < 64
-      (void)slot;
       if (task < H) {
         double t[O + 2];
 #pragma unroll
