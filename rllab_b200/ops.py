@@ -239,6 +239,15 @@ class PendingHost(object):
             self._host = None
         return self._val
 
+    def __del__(self):
+        # never read: hand the staging buffer back (a later copy into it is ordered behind this one on the stream)
+        host = getattr(self, "_host", None)
+        if host is not None:
+            try:
+                PendingHost._pool[self._key].append(host)
+            except Exception:
+                pass
+
 
 class LazyTriple(object):
     """(loss, mean KL, max KL) of one pass, read back lazily: indexing blocks on the readback event."""
