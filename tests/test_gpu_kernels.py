@@ -367,8 +367,19 @@ def _update_setup(dev, env_name, hidden, N=512, T=32):
 @pytest.mark.parametrize("env_name,hidden", [("cartpole", 32), ("point", 32), ("pendulum", 32), ("cartpole", 64)] +
                          ([("swimmer", 32), ("hopper", 64)] if "hopper" in ENVS else []))
 def test_loss_kl_grad_fvp_match_oracle(dev, env_name, hidden):
+    _check_update_kernels(dev, env_name, hidden, 512, 32)
+
+
+@pytest.mark.parametrize("env_name,hidden", [("cartpole", 32), ("cartpole", 64)])
+def test_update_kernels_ragged_batch(dev, env_name, hidden):
+    """B = 509 * 31 = 15 779 samples: odd (activation-cache rows unaligned -> scalar cache path) and not a multiple of the
+    128-sample tile (the last tile is partly masked)."""
+    _check_update_kernels(dev, env_name, hidden, 509, 31)
+
+
+def _check_update_kernels(dev, env_name, hidden, N, T):
     L = _L()
-    ops, env, dims, theta, b, batch = _update_setup(dev, env_name, hidden)
+    ops, env, dims, theta, b, batch = _update_setup(dev, env_name, hidden, N, T)
     dd = (env.O, hidden, hidden, env.A)
     B = b.B
     th32 = torch.tensor(theta, dtype=torch.float32, device=dev)
