@@ -83,6 +83,11 @@ class BatchPolopt(RLAlgorithm):
             self.policy.log_diagnostics(paths)
             self.baseline.log_diagnostics(paths)
 
+    def update_plot(self):
+        """batch_polopt.py:163-165: only ever called when plot=True, which the constructor rejects."""
+        if self.plot:
+            raise NotImplementedError("plotting is outside the B200 hot path")
+
     def init_opt(self):
         raise NotImplementedError
 

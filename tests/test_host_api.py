@@ -113,3 +113,41 @@ def test_logger_tabular_and_snapshot(tmp_path):
     assert d["itr"] == 0
     logger.set_snapshot_mode("none")
     logger.set_snapshot_dir(None)
+
+
+def test_plugin_api_surface_matches_reference():
+    """Constructor arguments (names, literal defaults) and public members of every mirrored class against the
+    reference's own source (tests/golden/reference_api.json, extracted with ast by tests/golden/make_api_golden.py).
+    Only Theano-symbolic members are exempt: this implementation has no symbolic graph (the C ABI replaces it)."""
+    import importlib
+    import inspect
+    import json
+    import os
+    api = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_api.json")))
+    exempt = {
+        "Box": {"new_tensor_variable"},
+        "DiagonalGaussian": {"kl_sym", "likelihood_ratio_sym", "log_likelihood_sym", "entropy_sym"},
+        "GaussianMLPPolicy": {"dist_info_sym", "get_reparam_action_sym"},
+        "FirstOrderOptimizer": {"optimize_gen"},      # generator form of the mini-batch loop; VPG uses optimize()
+    }
+    assert len(api) >= 14
+    for name, d in sorted(api.items()):
+        mod, cls = d["mirror"].rsplit(".", 1)
+        C = getattr(importlib.import_module(mod), cls)
+        params = {}
+        for k in C.__mro__:                            # the reference forwards **kwargs up its class chain as well
+            if "__init__" in k.__dict__:
+                for p in inspect.signature(k.__dict__["__init__"]).parameters.values():
+                    params.setdefault(p.name, p)
+        for a in (d["init"] or {"args": []})["args"]:
+            assert a["name"] in params, "%s.__init__ lacks the reference argument %r" % (name, a["name"])
+            if a["default"] and "literal" in a["default"]:
+                mine = params[a["name"]].default
+                assert mine is not inspect.Parameter.empty, (name, a["name"])
+                mine = list(mine) if isinstance(mine, tuple) else mine
+                assert mine == a["default"]["literal"], (name, a["name"], mine, a["default"]["literal"])
+        for m in d["methods"] + d["properties"]:
+            if m in exempt.get(name, ()):
+                assert not hasattr(C, m)               # keep the exemption list honest
+                continue
+            assert hasattr(C, m), "%s lacks the reference member %r" % (name, m)
