@@ -24,6 +24,17 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def require_defaults(cls_name, given, supported):
+    """The device kernels implement the reference envs at their default construction arguments; anything else is
+    rejected loudly rather than silently ignored."""
+    for k, v in given.items():
+        if k not in supported:
+            raise TypeError("%s() got an unexpected keyword argument %r" % (cls_name, k))
+        if v is not None and v != supported[k]:
+            raise NotImplementedError("%s(%s=%r): only the reference default %r is built into the CUDA dynamics"
+                                      % (cls_name, k, v, supported[k]))
+
+
 class LaneEnv(Env):
     """Base of the device-backed envs.  Subclasses set ENV_NAME and (optionally) HORIZON."""
     ENV_NAME = None

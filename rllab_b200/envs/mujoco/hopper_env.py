@@ -2,11 +2,20 @@
 import numpy as np
 
 from ...misc import logger
-from ..lane_env import LaneEnv
+from ..lane_env import LaneEnv, require_defaults
 
 
 class HopperEnv(LaneEnv):
     ENV_NAME = "hopper"
+
+    def __init__(self, alive_coeff=1, ctrl_cost_coeff=0.01, **kwargs):
+        # hopper_env.py:27-35 + MujocoEnv.__init__(action_noise=0.0, file_path=None, template_args=None)
+        require_defaults("HopperEnv", dict(kwargs, alive_coeff=alive_coeff, ctrl_cost_coeff=ctrl_cost_coeff),
+                         dict(alive_coeff=1, ctrl_cost_coeff=0.01, action_noise=0.0, file_path=None,
+                              template_args=None))
+        self.alive_coeff = alive_coeff
+        self.ctrl_cost_coeff = ctrl_cost_coeff
+        super(HopperEnv, self).__init__()
 
     def log_diagnostics(self, paths):
         progs = [path["observations"][-1][-3] - path["observations"][0][-3] for path in paths]

@@ -30,6 +30,11 @@ CLASSES = {
     "rllab/distributions/diagonal_gaussian.py": {
         "DiagonalGaussian": "rllab_b200.distributions.diagonal_gaussian.DiagonalGaussian"},
     "rllab/sampler/base.py": {"Sampler": "rllab_b200.sampler.base.Sampler"},
+    "rllab/envs/box2d/cartpole_env.py": {"CartpoleEnv": "rllab_b200.envs.box2d.cartpole_env.CartpoleEnv"},
+    "rllab/envs/mujoco/swimmer_env.py": {"SwimmerEnv": "rllab_b200.envs.mujoco.swimmer_env.SwimmerEnv"},
+    "rllab/envs/mujoco/hopper_env.py": {"HopperEnv": "rllab_b200.envs.mujoco.hopper_env.HopperEnv"},
+    "examples/point_env.py": {"PointEnv": "rllab_b200.envs.point_env.PointEnv"},
+    "rllab/envs/gym_env.py": {"GymEnv": "rllab_b200.envs.gym_env.GymEnv"},
 }
 
 

@@ -129,16 +129,24 @@ def test_plugin_api_surface_matches_reference():
         "DiagonalGaussian": {"kl_sym", "likelihood_ratio_sym", "log_likelihood_sym", "entropy_sym"},
         "GaussianMLPPolicy": {"dist_info_sym", "get_reparam_action_sym"},
         "FirstOrderOptimizer": {"optimize_gen"},      # generator form of the mini-batch loop; VPG uses optimize()
+        # simulator internals (Box2D generators, MuJoCo model accessors): the dynamics live in the CUDA kernels
+        "CartpoleEnv": {"compute_reward", "is_current_done"},
+        "SwimmerEnv": {"get_current_obs", "get_ori"},
+        "HopperEnv": {"get_current_obs"},
     }
-    assert len(api) >= 14
+    assert len(api) >= 19
     for name, d in sorted(api.items()):
         mod, cls = d["mirror"].rsplit(".", 1)
         C = getattr(importlib.import_module(mod), cls)
         params = {}
-        for k in C.__mro__:                            # the reference forwards **kwargs up its class chain as well
-            if "__init__" in k.__dict__:
-                for p in inspect.signature(k.__dict__["__init__"]).parameters.values():
-                    params.setdefault(p.name, p)
+        if inspect.isfunction(C):                      # GymEnv is a factory returning the device-backed PendulumEnv
+            params = dict(inspect.signature(C).parameters)
+            C = getattr(importlib.import_module(mod), "PendulumEnv")
+        else:
+            for k in C.__mro__:                        # the reference forwards **kwargs up its class chain as well
+                if "__init__" in k.__dict__:
+                    for p in inspect.signature(k.__dict__["__init__"]).parameters.values():
+                        params.setdefault(p.name, p)
         for a in (d["init"] or {"args": []})["args"]:
             assert a["name"] in params, "%s.__init__ lacks the reference argument %r" % (name, a["name"])
             if a["default"] and "literal" in a["default"]:
@@ -151,3 +159,20 @@ def test_plugin_api_surface_matches_reference():
                 assert not hasattr(C, m)               # keep the exemption list honest
                 continue
             assert hasattr(C, m), "%s lacks the reference member %r" % (name, m)
+
+
+def test_env_constructors_accept_reference_arguments_and_reject_other_values():
+    """hopper_env.py:27-35, swimmer_env.py:17-23, cartpole_env.py:13-24: the reference defaults are what the CUDA
+    dynamics implement; other values fail loudly (no silent fallback), unknown names are TypeErrors."""
+    from rllab_b200.envs.box2d.cartpole_env import CartpoleEnv
+    from rllab_b200.envs.mujoco.hopper_env import HopperEnv
+    from rllab_b200.envs.mujoco.swimmer_env import SwimmerEnv
+    assert SwimmerEnv(ctrl_cost_coeff=1e-2).ctrl_cost_coeff == 1e-2
+    h = HopperEnv(alive_coeff=1, ctrl_cost_coeff=0.01, action_noise=0.0)
+    assert (h.alive_coeff, h.ctrl_cost_coeff) == (1, 0.01)
+    assert CartpoleEnv(frame_skip=1).max_cart_pos == 2.4
+    for bad in (lambda: SwimmerEnv(ctrl_cost_coeff=0.1), lambda: HopperEnv(alive_coeff=2), lambda: CartpoleEnv(obs_noise=0.1)):
+        with pytest.raises(NotImplementedError):
+            bad()
+    with pytest.raises(TypeError):
+        HopperEnv(bogus=1)
