@@ -38,6 +38,26 @@ CLASSES = {
 }
 
 
+# reference file -> mirror source files that must record the same logger.record_tabular keys
+TABULAR = {
+    "rllab/sampler/base.py": ["rllab_b200/sampler/lane_sampler.py"],
+    "rllab/algos/vpg.py": ["rllab_b200/algos/vpg.py"],
+    "rllab/algos/npo.py": ["rllab_b200/algos/npo.py"],
+    "rllab/policies/gaussian_mlp_policy.py": ["rllab_b200/algos/batch_polopt.py"],
+    "rllab/envs/mujoco/swimmer_env.py": ["rllab_b200/envs/mujoco/swimmer_env.py"],
+    "rllab/envs/mujoco/hopper_env.py": ["rllab_b200/envs/mujoco/hopper_env.py"],
+}
+
+
+def tabular_keys(tree):
+    keys = []
+    for n in ast.walk(tree):
+        if (isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute) and n.func.attr == "record_tabular" and n.args
+                and isinstance(n.args[0], ast.Constant) and n.args[0].value not in keys):
+            keys.append(n.args[0].value)
+    return keys
+
+
 def literal(node):
     try:
         return {"literal": ast.literal_eval(node)}
@@ -74,9 +94,11 @@ def main():
                 api[node.name] = d
     missing = {c for cl in CLASSES.values() for c in cl} - set(api)
     assert not missing, missing
+    api["__tabular__"] = {rel: {"keys": tabular_keys(ast.parse(open(os.path.join(REF, rel)).read())), "mirrors": mirrors}
+                          for rel, mirrors in TABULAR.items()}
     with open(OUT, "w") as f:
         json.dump(api, f, indent=1, sort_keys=True, default=str)
-    print("wrote", OUT, len(api), "classes")
+    print("wrote", OUT, len(api) - 1, "classes")
 
 
 if __name__ == "__main__":

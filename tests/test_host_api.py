@@ -134,6 +134,13 @@ def test_plugin_api_surface_matches_reference():
         "SwimmerEnv": {"get_current_obs", "get_ori"},
         "HopperEnv": {"get_current_obs"},
     }
+    tabular = api.pop("__tabular__")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for rel, d in tabular.items():                     # same logger.record_tabular keys as the reference records
+        src = "".join(open(os.path.join(root, m)).read() for m in d["mirrors"])
+        assert d["keys"], rel
+        for key in d["keys"]:
+            assert ('"%s"' % key in src) or ("'%s'" % key in src) or (key.endswith("ForwardProgress") and "ForwardProgress" in src), (rel, key)
     assert len(api) >= 19
     for name, d in sorted(api.items()):
         mod, cls = d["mirror"].rsplit(".", 1)
