@@ -99,6 +99,23 @@ __device__ __forceinline__ void noise4(int kind, uint32_t seed, uint32_t iter, i
   }
 }
 
+// ---------------------------------------------------------------- experimental: weights through the constant bank
+// Build variant -DB200RL_CONST_WEIGHTS (make VARIANT=cw -> variants/libb200rl_cw.so, select with B200RL_LIB=...): the
+// thread-per-sample kernels read theta from a per-translation-unit __constant__ array, so that the weight operand of
+// every FFMA2 is a uniform-register pair filled by LDCU.128 instead of vector registers filled by LDS.128 (DESIGN.md
+// section 8).  NOT part of the default library: not yet measured on a GPU.
+#ifdef B200RL_CONST_WEIGHTS
+#define B200RL_CONST_MAXP 6144     // >= P of the largest compiled net (Hopper 64x64: 5 702)
+#define B200RL_DEFINE_CONST_THETA                                                                        \
+  __constant__ __align__(16) float c_theta[B200RL_CONST_MAXP];                                           \
+  static int upload_theta(const float* params_dev, int P, cudaStream_t st) {                             \
+    B200RL_REQUIRE(P <= B200RL_CONST_MAXP, "constant-weights variant: too many parameters");             \
+    B200RL_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_theta, params_dev, (size_t)P * sizeof(float), 0,         \
+                                              cudaMemcpyDeviceToDevice, st));                            \
+    return 0;                                                                                            \
+  }
+#endif
+
 // ---------------------------------------------------------------- math
 // tanh used by every kernel (rollout and update MUST share it so that the likelihood ratio is exactly 1 at
 // theta_old): CUDA's tanhf (<= 2 ulp; ~16 instructions with two MUFU ops).  The single definition lives here so that a

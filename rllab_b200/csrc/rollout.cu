@@ -64,6 +64,10 @@ struct RolloutArgs {
   float* log_std_out;
 };
 
+#ifdef B200RL_CONST_WEIGHTS
+B200RL_DEFINE_CONST_THETA
+#endif
+
 // One thread per lane; the whole T-step trajectory of a lane stays in that thread's registers.
 template <class Env, int H>
 __global__ void __launch_bounds__(ROLLOUT_THREADS, rollout_minblocks<Env, H>()) rollout_kernel(RolloutArgs a) {
@@ -71,10 +75,15 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, rollout_minblocks<Env, H>()) 
   // 32-wide: parameters only (static); 64-wide: + one activation column per thread for the rolled layer-2 loop
   constexpr int P4 = (N_::P + 3) & ~3;
   extern __shared__ __align__(16) float rollout_smem[];
+#ifdef B200RL_CONST_WEIGHTS
+  const float* sp = c_theta;
+  float* hcol = (H > 32) ? rollout_smem + P4 + threadIdx.x : nullptr;
+#else
   float* sp = rollout_smem;
   float* hcol = (H > 32) ? rollout_smem + P4 + threadIdx.x : nullptr;
   for (int i = threadIdx.x; i < N_::P; i += blockDim.x) sp[i] = a.params[i];
   __syncthreads();
+#endif
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   float std_[Env::A];
 #pragma unroll
@@ -217,6 +226,12 @@ __global__ void fill_noise_kernel(float* __restrict__ out, int rows, int row0, i
 template <class Env>
 static int launch_rollout(int h, const RolloutArgs& a, cudaStream_t st) {
   const int grid = (a.N + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
+#ifdef B200RL_CONST_WEIGHTS
+  if (h == 32 || h == 64) {
+    int rc = upload_theta(a.params, h == 32 ? Net<Env::O, 32, 32, Env::A>::P : Net<Env::O, 64, 64, Env::A>::P, st);
+    if (rc) return rc;
+  }
+#endif
   if (h == 32) {
     using N32 = Net<Env::O, 32, 32, Env::A>;
     rollout_kernel<Env, 32><<<grid, ROLLOUT_THREADS, ((N32::P + 3) & ~3) * sizeof(float), st>>>(a);

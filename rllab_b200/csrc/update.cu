@@ -395,16 +395,24 @@ __global__ void __launch_bounds__(UPD_THREADS) update_kernel(UpdArgs a) {
 
 // Surrogate loss + KL, one THREAD per sample (forward only: no cross-sample reduction of per-weight quantities, so
 // the thread-per-lane forward of the rollout kernel is the cheapest formulation; same canonical summation order).
+#ifdef B200RL_CONST_WEIGHTS
+B200RL_DEFINE_CONST_THETA
+#endif
 constexpr int LOSS_THREADS = 128;
 template <class N>
 constexpr int loss_minblocks() { return (N::H1 == 32 && N::O <= 4) ? 4 : 1; }   // 128 registers: 1.47 -> 1.28 ms (A/B)
 template <class N>
 __global__ void __launch_bounds__(LOSS_THREADS, loss_minblocks<N>()) loss_thread_kernel(UpdArgs a) {
   constexpr int O = N::O, A = N::A;
+#ifdef B200RL_CONST_WEIGHTS
+  const float* sp = c_theta;
+  __shared__ double red_scratch[3 * 32];
+#else
   __shared__ __align__(16) float sp[N::P];
   __shared__ double red_scratch[3 * 32];
   for (int i = threadIdx.x; i < N::P; i += blockDim.x) sp[i] = a.params[i];
   __syncthreads();
+#endif
   float ls_new[A], inv_std[A], var_new[A], var_new2[A], ls_old[A], inv_std_old[A], var_old[A];
   float sum_ls_new = 0.f, sum_ls_old = 0.f;
 #pragma unroll
@@ -549,6 +557,12 @@ int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, 
     if (g > MAX_PARTIAL_BLOCKS) g = MAX_PARTIAL_BLOCKS;
     grid = (int)g;
   }
+#ifdef B200RL_CONST_WEIGHTS
+  B200RL_DISPATCH_NET({
+    int rc_up = upload_theta(params_f32, NetT::P, st);
+    if (rc_up) return rc_up;
+  });
+#endif
   B200RL_DISPATCH_NET({ loss_thread_kernel<NetT><<<grid, LOSS_THREADS, 0, st>>>(a); });
   B200RL_LAUNCH_CHECK("loss_thread_kernel");
   // partial layout [grid][3] = (sum loss, sum kl, max kl): strided finalize

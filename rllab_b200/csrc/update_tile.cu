@@ -14,6 +14,9 @@
 namespace b200rl {
 
 constexpr int T_THREADS = 128, T_TILE = 128, T_LD = T_TILE + 4;
+#ifdef B200RL_CONST_WEIGHTS
+B200RL_DEFINE_CONST_THETA
+#endif
 
 
 template <class N, int MODE>
@@ -41,13 +44,19 @@ __global__ void __launch_bounds__(T_THREADS, tile_minblocks<N, MODE>()) update_t
   constexpr int O = N::O, H = 32, A = N::A, P = N::P, LD = T_LD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sf = reinterpret_cast<float*>(smem_raw);
+#ifdef B200RL_CONST_WEIGHTS
+  const float* sp = c_theta;               // the FVP tangent (sv) stays in shared memory in this variant
+#else
   float* sp = sf + SM::o_sp;
+#endif
   float* sv = sf + SM::o_sv;
   float* stage = sf + SM::o_stage;
   double* red_scratch = reinterpret_cast<double*>(smem_raw + SM::scratch_off);
   const int tid = threadIdx.x;
 
+#ifndef B200RL_CONST_WEIGHTS
   for (int i = tid; i < P; i += T_THREADS) sp[i] = a.params[i];
+#endif
   if constexpr (MODE == MODE_FVP)
     for (int i = tid; i < P; i += T_THREADS) sv[i] = (float)a.xvec[i];
   __syncthreads();
@@ -231,6 +240,12 @@ static int launch_tile(const UpdArgs& a, int* grid_out, cudaStream_t st) {
   const long long ntiles = (a.B + T_TILE - 1) / T_TILE;
   if (grid > ntiles) grid = ntiles;
   if (grid > MAX_PARTIAL_BLOCKS) grid = MAX_PARTIAL_BLOCKS;
+#ifdef B200RL_CONST_WEIGHTS
+  {
+    int rc_up = upload_theta(a.params, N::P, st);
+    if (rc_up) return rc_up;
+  }
+#endif
   update_tile_kernel<N, MODE><<<(unsigned)grid, T_THREADS, SM::bytes, st>>>(a);
   B200RL_LAUNCH_CHECK("update_tile_kernel");
   *grid_out = (int)grid;
