@@ -120,7 +120,20 @@ __device__ __forceinline__ void noise4(int kind, uint32_t seed, uint32_t iter, i
 // tanh used by every kernel (rollout and update MUST share it so that the likelihood ratio is exactly 1 at
 // theta_old): CUDA's tanhf (<= 2 ulp; ~16 instructions with two MUFU ops).  The single definition lives here so that a
 // cheaper variant, if one is ever adopted, replaces it in all kernels at once.
+#ifdef B200RL_FAST_TANH
+// experimental build variant (make VARIANT=ft): 1 - 2 / (2^(2 log2(e) x) + 1) with MUFU.EX2 + MUFU.RCP, 5 instructions
+// instead of tanhf's ~14; saturates correctly (+inf -> 1, 0 -> -1); absolute error <= ~4e-7 (relative accuracy is lost
+// near 0, which the activations do not need).  NumPy emulation: policy mean off by 8e-7 of its scale (tanhf: 7e-8).
+// NOT in the default library: the parity tests have not been run with it on a GPU.
+__device__ __forceinline__ float tanh_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
+#else
 __device__ __forceinline__ float tanh_f(float x) { return tanhf(x); }
+#endif
 
 // ---------------------------------------------------------------- reductions
 __device__ __forceinline__ double warp_sum(double v) {
