@@ -132,3 +132,19 @@ def test_lane_rollout_reproduces_reference_rollout_semantics(golden):
     assert np.array_equal(traj["obs"][:, :L, 0].T, g["pt_done_obs"])
     assert np.array_equal(traj["rew"][:L, 0], g["pt_done_rew"])
     assert traj["tstep"][L, 0] == 0 and np.array_equal(traj["obs"][:, L, 0], [0.05, -0.03])
+
+
+def test_swimmer_learning_curve_fixture_is_sane():
+    """tests/golden/oracle_swimmer_trpo_curve.json (make_swimmer_curve.py): the oracle's TRPO run on Swimmer that the GPU
+    learning check compares against -- every step accepted within the trust region, return improving."""
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_swimmer_trpo_curve.json")))
+    cfg, curve = d["config"], d["curve"]
+    assert (cfg["lanes"], cfg["horizon"], cfg["cg_iters"], cfg["step_size"]) == (1024, 500, 10, 0.01)
+    assert [r["itr"] for r in curve] == list(range(40))
+    assert all(r["NumTrajs"] == cfg["lanes"] for r in curve)                  # Swimmer never terminates early
+    assert all((not r["rejected"]) and 0 < r["MeanKL"] <= cfg["step_size"] for r in curve)
+    assert all(r["LossAfter"] < r["LossBefore"] for r in curve)
+    ret = np.array([r["AverageReturn"] for r in curve])
+    assert ret[0] < 0 < ret[10] < ret[20] < ret[39] and ret[39] > 30
