@@ -1,6 +1,6 @@
 """GPU side of north_star's Swimmer learning check: TRPO on the device with the configuration of
 tests/golden/oracle_swimmer_trpo_curve.json (same lanes, horizon, Philox seed, policy seed), AverageReturn per iteration
-printed next to the float64 oracle's curve.  Run on a B200:  python scripts/swimmer_curve_gpu.py [n_itr]
+printed next to the float64 oracle's curve.  Run on a B200:  python scripts/swimmer_curve_gpu.py [n_itr] [swimmer|hopper]
 
 Iteration 0 sees the same initial policy and the same noise as the oracle run, so its AverageReturn must agree to the
 planar-dynamics tolerance; later iterations are two independent stochastic-optimisation trajectories of the same
@@ -15,17 +15,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(n_itr):
+def main(n_itr, env_name="swimmer"):
     from rllab_b200.algos.trpo import TRPO
     from rllab_b200.baselines.linear_feature_baseline import LinearFeatureBaseline
+    from rllab_b200.envs.mujoco.hopper_env import HopperEnv
     from rllab_b200.envs.mujoco.swimmer_env import SwimmerEnv
     from rllab_b200.envs.normalized_env import normalize
     from rllab_b200.misc import logger
     from rllab_b200.policies.gaussian_mlp_policy import GaussianMLPPolicy
-    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_swimmer_trpo_curve.json")))
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_%s_trpo_curve.json" % env_name)))
     cfg, curve = gold["config"], gold["curve"]
     logger.set_quiet(True)
-    env = normalize(SwimmerEnv())
+    env = normalize(HopperEnv() if env_name == "hopper" else SwimmerEnv())
     policy = GaussianMLPPolicy(env.spec, hidden_sizes=tuple(cfg["hidden"]), seed=cfg["policy_seed"])
     algo = TRPO(env=env, policy=policy, baseline=LinearFeatureBaseline(env.spec), batch_size=cfg["lanes"] * cfg["horizon"],
                 max_path_length=cfg["horizon"], n_itr=n_itr, discount=cfg["discount"], gae_lambda=cfg["gae_lambda"],
@@ -48,4 +49,4 @@ def main(n_itr):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 40)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 40, sys.argv[2] if len(sys.argv) > 2 else "swimmer")

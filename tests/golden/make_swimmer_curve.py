@@ -4,7 +4,8 @@ LaneSampler(seed=SEED) on the GPU).  Purpose: north_star's "TRPO AverageReturn o
 matched sample count" -- the reference's MuJoCo Swimmer cannot run in this container, so the comparison
 target is the oracle restatement (oracle/planar.py), at N lanes x T steps per iteration.
 
-Run (CPU only, ~1 min per iteration):  python tests/golden/make_swimmer_curve.py [n_itr]
+Run (CPU only, ~2 min per iteration):  python tests/golden/make_swimmer_curve.py [n_itr] [swimmer|hopper]
+(hopper: the cfg4 net (64,64), same keys; written to oracle_hopper_trpo_curve.json)
 """
 import json
 import os
@@ -18,21 +19,23 @@ sys.path.insert(0, ROOT)
 
 from oracle import envs as E, optim as OPT, philox as PH, policy as P, sampler as S  # noqa: E402
 
-N, T, SEED, POLICY_SEED, HIDDEN = 1024, 500, 7, 3, 32
+N, T, SEED, POLICY_SEED = 1024, 500, 7, 3
 DISCOUNT, GAE_LAMBDA, STEP_SIZE, CG_ITERS = 0.99, 1.0, 0.01, 10
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_swimmer_trpo_curve.json")
 
 
-def main(n_itr):
-    env = E.make("swimmer")
+def main(n_itr, env_name="swimmer"):
+    HIDDEN = 64 if env_name == "hopper" else 32
+    OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_%s_trpo_curve.json" % env_name)
+    env = E.make(env_name)
     dims = P.Dims(env.O, (HIDDEN, HIDDEN), env.A)
     theta = P.init_params(dims, np.random.RandomState(POLICY_SEED))      # == GaussianMLPPolicy(..., seed=POLICY_SEED)
     coeffs = None
     rows = []
     for itr in range(n_itr):
         t0 = time.time()
-        eps = PH.normal_from_raw(PH.raw_block(T, 0, env.A, N, 0, SEED, itr, 0))
-        rr = PH.normal_from_raw(PH.raw_block(T + 1, 0, env.K, N, 0, SEED, itr, 1))
+        Ae, Ke = env.A + (env.A & 1), env.K + (env.K & 1)        # Box-Muller pairs: pad odd counts, drop the extra
+        eps = PH.normal_from_raw(PH.raw_block(T, 0, Ae, N, 0, SEED, itr, 0))[:, :env.A]
+        rr = PH.normal_from_raw(PH.raw_block(T + 1, 0, Ke, N, 0, SEED, itr, 1))[:, :env.K]
         traj = S.rollout_lanes(env, theta, dims, N, T, T, eps, rr)
         out = S.process_samples_lanes(traj, coeffs, DISCOUNT, GAE_LAMBDA, center_adv=True)
         coeffs = S.lfb_fit_lanes(traj["obs"], traj["tstep"], out["ret"])
@@ -46,7 +49,7 @@ def main(n_itr):
                          rejected=bool(info["rejected"]), seconds=time.time() - t0))
         print(rows[-1], flush=True)
         with open(OUT, "w") as f:
-            json.dump(dict(config=dict(env="swimmer", lanes=N, horizon=T, seed=SEED, policy_seed=POLICY_SEED,
+            json.dump(dict(config=dict(env=env_name, lanes=N, horizon=T, seed=SEED, policy_seed=POLICY_SEED,
                                        hidden=[HIDDEN, HIDDEN], discount=DISCOUNT, gae_lambda=GAE_LAMBDA,
                                        step_size=STEP_SIZE, cg_iters=CG_ITERS, baseline="LinearFeatureBaseline",
                                        arithmetic="float64 NumPy oracle (oracle/planar.py, oracle/optim.py)"),
@@ -54,4 +57,4 @@ def main(n_itr):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 40)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 40, sys.argv[2] if len(sys.argv) > 2 else "swimmer")
