@@ -148,3 +148,18 @@ def test_swimmer_learning_curve_fixture_is_sane():
     assert all(r["LossAfter"] < r["LossBefore"] for r in curve)
     ret = np.array([r["AverageReturn"] for r in curve])
     assert ret[0] < 0 < ret[10] < ret[20] < ret[39] and ret[39] > 30
+
+
+def test_hopper_learning_curve_fixture_is_sane():
+    """tests/golden/oracle_hopper_trpo_curve.json: the same oracle TRPO run on Hopper with the cfg4 net (64,64)."""
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_hopper_trpo_curve.json")))
+    cfg, curve = d["config"], d["curve"]
+    assert (cfg["env"], cfg["hidden"], cfg["lanes"], cfg["horizon"]) == ("hopper", [64, 64], 1024, 500)
+    assert [r["itr"] for r in curve] == list(range(40))
+    assert all((not r["rejected"]) and 0 < r["MeanKL"] <= cfg["step_size"] for r in curve)
+    ret = np.array([r["AverageReturn"] for r in curve])
+    ntraj = np.array([r["NumTrajs"] for r in curve])
+    assert np.all(np.diff(ret) > 0) and ret[-1] > 200          # monotone improvement: the hopper stays up longer ...
+    assert ntraj[0] > 10 * ntraj[-1] >= cfg["lanes"]           # ... so the same 512 000 samples hold far fewer paths
