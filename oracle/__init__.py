@@ -17,5 +17,7 @@ Pinning status (see DESIGN.md "Oracle"):
   * PARITY UNPINNED (third-party arithmetic absent from /root/reference and not
     installable here): Theano autodiff of the MLP (checked instead against
     finite differences and torch.autograd in tests), Lasagne Adam, Box2D
-    CartPole, gym Pendulum-v0, MuJoCo-1.31 Swimmer/Hopper.
+    CartPole, gym Pendulum-v0, MuJoCo-1.31 Swimmer/Hopper (their MODEL constants
+    are pinned to vendor/mujoco_models/*.xml by tests/golden/reference_mujoco_models.json;
+    the dynamics algorithm is a restatement of the published pipeline).
 """

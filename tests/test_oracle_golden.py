@@ -163,3 +163,85 @@ def test_hopper_learning_curve_fixture_is_sane():
     ntraj = np.array([r["NumTrajs"] for r in curve])
     assert np.all(np.diff(ret) > 0) and ret[-1] > 200          # monotone improvement: the hopper stays up longer ...
     assert ntraj[0] > 10 * ntraj[-1] >= cfg["lanes"]           # ... so the same 512 000 samples hold far fewer paths
+
+
+def test_planar_models_match_reference_mujoco_xml():
+    """oracle/planar.py's Swimmer / Hopper model constants re-derived from the reference's own model files
+    (tests/golden/reference_mujoco_models.json <- vendor/mujoco_models/*.xml, make_mujoco_model_golden.py)."""
+    import json
+    import os
+    from oracle import planar as PL
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_mujoco_models.json")))
+
+    def check(name, model, plane, hinge_names, geom_density):
+        x = ref[name]
+        ix, iy = plane                                           # which world axes span the model's plane
+        bodies = x["bodies"]
+        assert len(bodies) == model.n
+        assert model.dt == x["option"]["timestep"][0]
+        assert model.rk4 == (x["option"]["integrator"] == "RK4")
+        assert model.frame_skip == int(x["custom"].get("frame_skip", [1])[0])
+        assert model.density == x["option"].get("density", [0.0])[0]
+        assert model.viscosity == x["option"].get("viscosity", [0.0])[0]
+        global_coords = x["compiler"]["coordinate"] == "global"
+        jdef = x["default"].get("joint", {})
+        hinge_world = []                                         # world position of each body's hinge (reference pose)
+        origin_world = []
+        for b in bodies:
+            hinge = [j for j in b["joints"] if j["name"] == hinge_names[len(hinge_world)]][0]
+            if global_coords:
+                hw, ow = np.array(hinge["pos"]), np.array(b["pos"])
+            else:                                                # local: positions relative to the parent body frame
+                parent = [i for i, p in enumerate(bodies) if p["name"] == b["parent"]]
+                base = origin_world[parent[0]] if parent else np.zeros(3)
+                ow = base + np.array(b["pos"])
+                hw = ow + np.array(hinge["pos"])
+            hinge_world.append(hw), origin_world.append(ow)
+        for i, b in enumerate(bodies):
+            g = b["geoms"][0]
+            p0, p1 = np.array(g["fromto"][:3]), np.array(g["fromto"][3:])
+            if not global_coords:
+                p0, p1 = p0 + origin_world[i], p1 + origin_world[i]
+            r, L = g["size"][0], np.linalg.norm(p1 - p0)
+            mass, Ip, Ia = PL.capsule(r, L, g.get("density", [geom_density])[0])
+            np.testing.assert_allclose([model.mass[i], model.Ip[i], model.Ia[i]], [mass, Ip, Ia], rtol=1e-12)
+            com = 0.5 * (p0 + p1) - hinge_world[i]
+            np.testing.assert_allclose(model.c[i], (com[ix], com[iy]), atol=1e-12)
+            axis = (p1 - p0) / L
+            np.testing.assert_allclose(np.abs(model.long_axis[i]), np.abs((axis[ix], axis[iy])), atol=1e-12)
+            parent = [k for k, p in enumerate(bodies) if p["name"] == b["parent"]]
+            anchor = hinge_world[i] - (hinge_world[parent[0]] if parent else hinge_world[i])
+            np.testing.assert_allclose(model.a[i], (anchor[ix], anchor[iy]), atol=1e-12)
+            bo = origin_world[i] - hinge_world[i]
+            np.testing.assert_allclose(model.bo[i], (bo[ix], bo[iy]), atol=1e-12)
+            hinge = [j for j in b["joints"] if j["name"] == hinge_names[i]][0]
+            limited = hinge.get("limited", jdef.get("limited", "false")) == "true" and "range" in hinge
+            if limited:
+                np.testing.assert_allclose(model.limits[i], np.deg2rad(hinge["range"]), rtol=1e-12)
+            else:
+                assert model.limits[i] is None
+        # degrees of freedom in qpos order = joint order of the XML
+        joints = [j for b in bodies for j in b["joints"]]
+        assert len(joints) == len(model.armature) == len(model.damping) == len(model.q0)
+        for k, j in enumerate(joints):
+            assert model.armature[k] == j.get("armature", jdef.get("armature", [0.0]))[0], j["name"]
+            assert model.damping[k] == j.get("damping", jdef.get("damping", [0.0]))[0], j["name"]
+            assert model.q0[k] == j.get("ref", [0.0])[0], j["name"]
+        act = [a["joint"] for a in x["actuators"]]
+        assert [hinge_names[i] for i in model.act] == act
+        assert all(a["ctrlrange"] == [-model.ctrl_lim, model.ctrl_lim] for a in x["actuators"])
+        return bodies, hinge_world
+
+    sw = PL.swimmer_model()
+    check("swimmer", sw, (0, 1), ["rot", "rot2", "rot3"], 1000.0)
+    hp = PL.hopper_model()
+    bodies, hinge_world = check("hopper", hp, (0, 2), ["rooty", "thigh_joint", "leg_joint", "foot_joint"], 1000.0)
+    assert hp.gravity == (0.0, -9.81)                            # MuJoCo's default gravity, along -z
+    gdef = ref["hopper"]["default"]["geom"]
+    foot = bodies[3]["geoms"][0]
+    assert hp.mu == foot["friction"][0] and hp.margin == gdef["margin"][0]
+    assert list(hp.con_solref) == gdef["solref"] and list(hp.con_solimp) == gdef["solimp"]
+    ends = [np.array(foot["fromto"][:3]) - hinge_world[3], np.array(foot["fromto"][3:]) - hinge_world[3]]
+    for c, e in zip(hp.contacts, ends):                          # the two end spheres of the foot capsule
+        assert c["body"] == 3 and c["r"] == foot["size"][0]
+        np.testing.assert_allclose(c["e"], (e[0], e[2]), atol=1e-12)
