@@ -245,3 +245,25 @@ def test_planar_models_match_reference_mujoco_xml():
     for c, e in zip(hp.contacts, ends):                          # the two end spheres of the foot capsule
         assert c["body"] == 3 and c["r"] == foot["size"][0]
         np.testing.assert_allclose(c["e"], (e[0], e[2]), atol=1e-12)
+
+
+def test_cartpole_model_matches_reference_box2d_template():
+    """oracle/envs.py::CartPoleEnv's reduced-coordinate constants re-derived from the reference's Box2D model template and
+    env class (tests/golden/reference_cartpole_model.json <- models/cartpole.xml.mako, cartpole_env.py)."""
+    import json
+    import os
+    from oracle import envs as E
+    r = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cartpole_model.json")))
+    e = E.CartPoleEnv
+    assert r["densities"] == [1.0, 1.0]
+    np.testing.assert_allclose(e.M, r["densities"][0] * r["cart_width"] * r["cart_height"], rtol=1e-12)     # box area x density
+    np.testing.assert_allclose(e.m, r["densities"][1] * r["pole_width"] * r["pole_height"], rtol=1e-12)
+    # the pole rectangle runs from the hinge (0, 0) to (0, pole_height): COM half-way up, hinge on the cart's top edge
+    assert r["pole_vertices_expr"] == "compute_rect_vertices((0, 0), (0, pole_height), pole_width/2)"
+    assert r["pole_anchor_is_cart_top"]
+    np.testing.assert_allclose(e.l, r["pole_height"] / 2, rtol=1e-12)
+    np.testing.assert_allclose(e.I, e.m * (r["pole_width"] ** 2 + r["pole_height"] ** 2) / 12.0, rtol=1e-12)
+    assert e.dt_ == r["timestep"]
+    assert (e.lb[0], e.ub[0]) == tuple(r["ctrllimit"])
+    assert e.bounds == (r["max_cart_pos"], r["max_cart_speed"], r["max_pole_angle"], r["max_pole_speed"])
+    assert e.reset_range == r["reset_range"]
