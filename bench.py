@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=None, help="lanes per GPU (default: the workload's)")
     ap.add_argument("--horizon", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short TRPO workloads reported under extra.workloads")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
@@ -175,36 +176,42 @@ def main():
     import numpy as np
     import torch
     from rllab_b200 import _lib as L
-    from rllab_b200.algos.trpo import TRPO
-    from rllab_b200.algos.vpg import VPG
-    from rllab_b200.baselines.linear_feature_baseline import LinearFeatureBaseline
+    from rllab_b200 import ops
     from rllab_b200.misc import logger
     from rllab_b200.parallel import Comm
-    from rllab_b200.policies.gaussian_mlp_policy import GaussianMLPPolicy
 
     L.load()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     comm = Comm()
     logger.set_quiet(True)
-    np.random.seed(1)
-    env = make_env(env_name)
-    policy = GaussianMLPPolicy(env.spec, hidden_sizes=(hidden, hidden), seed=1)
-    baseline = LinearFeatureBaseline(env.spec)
-    n_total = lanes * world
-    kw = dict(env=env, policy=policy, baseline=baseline, batch_size=n_total * T, max_path_length=T, n_itr=10 ** 9,
-              discount=0.99, sampler_args=dict(n_envs=n_total, seed=1, comm=comm))
-    algo = VPG(**kw) if algo_name == "vpg" else TRPO(step_size=0.01, **kw)
-    algo.start_worker()
-    algo.init_opt()
-    steps_per_iter = n_total * T
     dev = torch.device("cuda", local_rank)
 
     def sync_all():
         comm.barrier()
         torch.cuda.synchronize()
 
-    def run(n, itr0, e2e):
+    def build(workload, lanes_override=None, horizon_override=None, the_comm=comm, seed=1):
+        from rllab_b200.algos.trpo import TRPO
+        from rllab_b200.algos.vpg import VPG
+        from rllab_b200.baselines.linear_feature_baseline import LinearFeatureBaseline
+        from rllab_b200.policies.gaussian_mlp_policy import GaussianMLPPolicy
+        env_n, algo_n, ln, hz, hid, _ = WORKLOADS[workload]
+        ln, hz = lanes_override or ln, horizon_override or hz
+        np.random.seed(1)
+        env = make_env(env_n)
+        policy = GaussianMLPPolicy(env.spec, hidden_sizes=(hid, hid), seed=1)
+        baseline = LinearFeatureBaseline(env.spec)
+        w = the_comm.world_size if the_comm.active else 1
+        n_total = ln * w
+        kw = dict(env=env, policy=policy, baseline=baseline, batch_size=n_total * hz, max_path_length=hz, n_itr=10 ** 9,
+                  discount=0.99, sampler_args=dict(n_envs=n_total, seed=seed, comm=the_comm))
+        algo = VPG(**kw) if algo_n == "vpg" else TRPO(step_size=0.01, **kw)
+        algo.start_worker()
+        algo.init_opt()
+        return algo, policy, baseline, n_total * hz
+
+    def run(algo, policy, n, itr0, e2e):
         """n iterations; returns elapsed ms on this rank (CUDA events on the launching stream)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         host_theta = policy.get_param_values()
@@ -220,26 +227,62 @@ def main():
         sync_all()
         return ev0.elapsed_time(ev1)
 
+    def max_over_ranks(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        comm.all_reduce_max(t)
+        return [float(x) for x in t.cpu().numpy()]
+
+    algo, policy, baseline, steps_per_iter = build(args.workload, args.lanes, args.horizon)
     itr = 0
-    run(args.warmup, itr, False)
+    run(algo, policy, args.warmup, itr, False)
     itr += args.warmup
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    k0 = L.kernel_launches()
-    ms_dev = run(args.steps, itr, False)
+    k0, c0 = L.kernel_launches(), comm.n_collectives
+    ms_dev = run(algo, policy, args.steps, itr, False)
     launches = (L.kernel_launches() - k0) / args.steps
+    collectives = (comm.n_collectives - c0) / args.steps
     itr += args.steps
-    from rllab_b200 import ops
     d2h0 = ops.PendingHost.bytes_total
-    ms_e2e = run(args.steps, itr, True)
+    ms_e2e = run(algo, policy, args.steps, itr, True)
     d2h_stats = (ops.PendingHost.bytes_total - d2h0) / args.steps    # statistics / loss triples read back per iteration
     itr += args.steps
     clk = clocks.stop() if clocks else None
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
-    comm.all_reduce_max(t)
-    ms_dev, ms_e2e = (float(x) for x in t.cpu().numpy())
+    ms_dev, ms_e2e = max_over_ranks(ms_dev, ms_e2e)
 
-    # ---- per-kernel timing of the same iteration (CUDA events around each library call), for the roofline
-    from rllab_b200 import ops
+    # ---- replicas must stay bit-identical: every rank applies the same update to the same all-reduced vectors
+    theta_dev = policy.theta64
+    replicas_identical = True
+    if comm.active:
+        gathered = [torch.empty_like(theta_dev) for _ in range(world)]
+        comm.dist.all_gather(gathered, theta_dev)
+        replicas_identical = all(bool(torch.equal(gathered[0], g)) for g in gathered)
+        assert replicas_identical, "policy parameters differ across ranks"
+
+    # ---- rank-count invariance on a small problem: the sharded run of this job reproduces, on every rank, the
+    # single-process run of the same total lanes (Philox is keyed by the GLOBAL lane; reductions are float64, rank order)
+    shard_check = None
+    if comm.active:
+        class _Solo(Comm):                                   # world-size-1 communicator inside this process
+            def __init__(self):
+                self.world_size, self.rank, self.local_rank, self.active = 1, 0, local_rank, False
+                self._gather_bufs, self.n_collectives, self._owns_group = {}, 0, False
+        small = "cartpole_vpg_65536x200"
+        a_sh, p_sh, _, _ = build(small, 1024, 50, comm, seed=5)
+        a_solo, p_solo, _, _ = build(small, 1024 * world, 50, _Solo(), seed=5)
+        for i in range(3):
+            a_sh.train_itr(i)
+            a_solo.train_itr(i)
+        torch.cuda.synchronize()
+        t_sh, t_solo = p_sh.get_param_values(), p_solo.get_param_values()
+        rel = float(np.max(np.abs(t_sh - t_solo)) / np.max(np.abs(t_solo)))
+        rel = max_over_ranks(rel)[0]
+        shard_check = dict(workload="cartpole VPG, %d lanes x 50 steps, 3 iterations" % (1024 * world),
+                           max_rel_diff_vs_single_process=rel)
+        assert rel < 1e-9, "sharded run differs from the single-process run: %g" % rel
+
+    # ---- per-kernel timing of the same iteration (CUDA events around each library call), for the rooflines
+    env_name, algo_name, lanes, T, hidden, alg_bytes = WORKLOADS[args.workload]
+    lanes, T = args.lanes or lanes, args.horizon or T
     b = algo.sampler.batch
     dims = policy.dims
 
@@ -254,46 +297,99 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
+    # FP32 roofline of this box, measured here: 16 independent fma.rn.f32x2 chains per thread, no memory traffic
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    import ctypes
+    fma = ctypes.c_longlong(0)
+    def _ffma():
+        L.call("b200rl_bench_ffma2", 4096, L.ptr(sink), ctypes.byref(fma), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    ms_ffma = timed(_ffma, reps=3)
+    fp32_peak = 2.0 * fma.value / (ms_ffma * 1e-3) / 1e12         # TFLOP/s (1 FMA = 2 flop)
+    hbm_peak, hbm_src = measured_peaks()
+
     g = torch.zeros(policy.n_params, dtype=torch.float64, device=dev)
     out3 = torch.zeros(3, dtype=torch.float64, device=dev)
     loss_kind = L.LOSS_VPG if algo_name == "vpg" else L.LOSS_TRPO
-    O, A = policy.obs_dim, policy.action_dim
+    O, A, h = policy.obs_dim, policy.action_dim, hidden
     samp_bytes = 4 * (O + 3 * A + 1)
+    F = 2.0 * (O * h + h * h + h * A)                               # flops of one policy forward
+    n_valid = float(b.count.cpu()[0]) if b.masked else float(b.B_global)
     kern = {}
     kern["rollout"] = dict(ms=timed(lambda: ops.rollout(algo.sampler.env_kind, policy.theta32, hidden, hidden,
                                                         policy.min_std, b, T, None, None, 1, 12345, algo.sampler.lane0)),
-                           bytes=alg_bytes * b.B, per_iter=1)
+                           bytes=alg_bytes * b.B, flops=F * b.B, per_iter=1, bound="fp32_issue")
     w = baseline.device_weights(b.O, dev)
-    kern["process_samples"] = dict(ms=timed(lambda: ops.process_samples(b, w, 0.99, 1.0)),
-                                   bytes=(4 * O + 4 + 1 + 2 + 12) * b.B, per_iter=1)
-    gram = torch.empty(((2 * O + 5) * (2 * O + 6) // 2,), dtype=torch.float64, device=dev)
-    kern["lfb_gram"] = dict(ms=timed(lambda: ops.lfb_gram(b, gram)), bytes=(4 * O + 2 + 4) * b.B, per_iter=1)
-    kern["loss_kl"] = dict(ms=timed(lambda: ops.loss_kl(loss_kind, policy.theta32, dims, policy.min_std, b,
-                                                        1.0 / b.B_global, out3)),
-                           bytes=samp_bytes * b.B, per_iter=1 if algo_name == "vpg" else 2)
-    kern["grad"] = dict(ms=timed(lambda: ops.grad(loss_kind, policy.theta32, dims, policy.min_std, b,
-                                                  1.0 / b.B_global, g)), bytes=samp_bytes * b.B, per_iter=1)
+    drop = bool(algo.whole_paths)
+    kern["process_samples"] = dict(ms=timed(lambda: ops.process_samples(b, w, 0.99, 1.0, drop_cut_paths=drop)),
+                                   bytes=(4 * O + 4 + 1 + 2 + 12) * b.B, flops=0.0, per_iter=1, bound="hbm")
+    gram = torch.empty_like(b.gram)
+    kern["lfb_gram"] = dict(ms=timed(lambda: ops.lfb_gram(b, gram)), bytes=(4 * O + 2 + 4 + 1) * b.B, flops=0.0,
+                            per_iter=1, bound="hbm")
+    kern["loss_kl"] = dict(ms=timed(lambda: ops.loss_kl(loss_kind, policy.theta32, dims, policy.min_std, b, out3)),
+                           bytes=samp_bytes * b.B, flops=F * b.B, per_iter=1 if algo_name == "vpg" else 2,
+                           bound="fp32_issue")
+    kern["grad"] = dict(ms=timed(lambda: ops.grad(loss_kind, policy.theta32, dims, policy.min_std, b, g)),
+                        bytes=samp_bytes * b.B, flops=(2 * F + 2.0 * (h * A + h * h)) * b.B, per_iter=1,
+                        bound="fp32_issue")
     if algo_name == "trpo":
         x = torch.randn(policy.n_params, dtype=torch.float64, device=dev)
         Hx = torch.zeros_like(x)
-        kern["fvp"] = dict(ms=timed(lambda: ops.fvp(policy.theta32, dims, policy.min_std, b, x, 1.0 / b.B_global,
-                                                    1e-5, 1.0, Hx)), bytes=4 * O * b.B, per_iter=11)
+        hc = b.hcache(h, h)
+        ops.grad(loss_kind, policy.theta32, dims, policy.min_std, b, g, None, hc)
+        fvp_flops = (2.0 * O * h + 4.0 * h * h + 4.0 * h * A + 2.0 * (h * A + h * h) + F) * b.B
+        kern["fvp"] = dict(ms=timed(lambda: ops.fvp(policy.theta32, dims, policy.min_std, b, x, 1e-5, 1.0, Hx, hc)),
+                           bytes=(4 * O + 8 * h) * b.B, flops=fvp_flops, per_iter=11, bound="fp32_issue")
     for k, v in kern.items():
         v["GBps"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+        v["TFLOPs"] = v["flops"] / (v["ms"] * 1e-3) / 1e12
+        v["frac"] = (v["GBps"] / hbm_peak) if v["bound"] == "hbm" else (v["TFLOPs"] / fp32_peak)
         v["share_of_step"] = v["ms"] * v["per_iter"] / (ms_dev / args.steps)
     dom = max(kern, key=lambda k: kern[k]["ms"] * kern[k]["per_iter"])
-    peak, peak_src = measured_peaks()
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this exact
-    # workload (profiles/r01b_ncu_summary.md); only quoted when the workload geometry is the profiled one
-    NCU_TRAFFIC = {("cartpole_vpg_65536x200", "grad"): 3.71e8, ("cartpole_vpg_65536x200", "rollout"): 3.48e8,
-                   ("cartpole_vpg_65536x200", "loss_kl"): 3.71e8, ("cartpole_vpg_65536x200", "process_samples"): 4.31e8}
-    traffic = NCU_TRAFFIC.get((args.workload, dom)) if (args.lanes is None and args.horizon is None) else None
-    roofline = dict(bound="hbm", kernel=dom, achieved=kern[dom]["GBps"], peak=peak, unit="GB/s",
-                    frac=kern[dom]["GBps"] / peak, traffic=traffic, peak_source=peak_src,
-                    algorithmic_bytes_per_launch=kern[dom]["bytes"], launch_ms=kern[dom]["ms"],
-                    note="per-kernel CUDA-event times of this run; the policy passes are FP32-issue bound, not HBM "
-                         "bound (DESIGN.md 'Rooflines')")
+    # dram bytes per launch from the ncu --set full capture of the shipped build (profiles/r02_traffic.json, written by
+    # scripts/ncu_traffic.py from the committed capture); only quoted for the profiled geometry
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath) and args.lanes is None and args.horizon is None:
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    kd = kern[dom]
+    if kd["bound"] == "hbm":
+        roofline = dict(bound="hbm", kernel=dom, achieved=kd["GBps"], peak=hbm_peak, unit="GB/s", frac=kd["frac"],
+                        traffic=traffic, peak_source=hbm_src)
+    else:
+        roofline = dict(bound="fp32_issue", kernel=dom, achieved=kd["TFLOPs"], peak=fp32_peak, unit="TFLOP/s",
+                        frac=kd["frac"], traffic=traffic,
+                        peak_source="measured in this run: b200rl_bench_ffma2 (independent fma.rn.f32x2 chains, no memory)",
+                        algorithmic_flops_per_launch=kd["flops"], algorithmic_bytes_per_launch=kd["bytes"],
+                        hbm_GBps=kd["GBps"], hbm_frac=kd["GBps"] / hbm_peak,
+                        note="the policy passes are bound by FP32 / instruction issue (%.0f flop per byte), not by HBM; "
+                             "the HBM-bound kernel of the step is process_samples, reported under roofline_hbm" %
+                             (kd["flops"] / max(kd["bytes"], 1)))
+    kp = kern["process_samples"]
+    roofline_hbm = dict(bound="hbm", kernel="process_samples", achieved=kp["GBps"], peak=hbm_peak, unit="GB/s",
+                        frac=kp["frac"], peak_source=hbm_src, algorithmic_bytes_per_launch=kp["bytes"],
+                        launch_ms=kp["ms"])
+
+    # ---- the other BASELINE configs that fit one GPU, a few iterations each (TRPO workloads: cfg3, cfg4 share)
+    extra = {}
+    if args.workload == "cartpole_vpg_65536x200" and not args.no_extra and args.lanes is None:
+        for wl in ("swimmer_trpo_16384x500", "hopper_trpo_4096x500"):
+            a2, p2, _, spi = build(wl)
+            run(a2, p2, 3, 0, False)
+            k1 = L.kernel_launches()
+            ms2 = run(a2, p2, 3, 3, False)
+            l2 = (L.kernel_launches() - k1) / 3
+            ms2 = max_over_ranks(ms2)[0]
+            extra[wl] = dict(ms_per_step=ms2 / 3, value=spi * 3 / (ms2 * 1e-3), unit="env-steps/s", steps=3, warmup=3,
+                             gpu_launches=l2, samples_per_step=spi,
+                             AverageReturn=a2.sampler.stats.get("AverageReturn"),
+                             backtrack_iters=a2.optimizer.last_info.get("n_iter"),
+                             MeanKL=a2.optimizer.last_info.get("constraint_val"))
+            a2.shutdown_worker()
     if rank != 0:
+        comm.close()
         return
     value = steps_per_iter * args.steps / (ms_dev * 1e-3)
     e2e_value = steps_per_iter * args.steps / (ms_e2e * 1e-3)
@@ -305,13 +401,18 @@ def main():
         data="synthetic", impl="b200",
         config=dict(workload=args.workload, env=env_name, algo=algo_name, lanes_per_gpu=lanes, horizon=T,
                     hidden=[hidden, hidden], samples_per_step=steps_per_iter, parallelism="lanes sharded x%d" % world,
+                    whole_paths=bool(algo.whole_paths), valid_samples_per_step=n_valid,
                     l2="trajectory buffers (%.0f MB/GPU) exceed the 126 MB L2" % (b.B * (alg_bytes + 14) / 1e6)),
         e2e=dict(value=e2e_value, unit="env-steps/s", ms_per_step=ms_e2e / args.steps,
                  h2d_bytes_per_step=8 * P_, d2h_bytes_per_step=8 * P_ + d2h_stats),
-        gpu_launches=launches, clocks=clk, roofline=roofline,
-        kernels={k: dict(ms=round(v["ms"], 4), GBps=round(v["GBps"], 1), per_iter=v["per_iter"],
-                         share_of_step=round(v["share_of_step"], 3)) for k, v in kern.items()},
+        gpu_launches=launches, collectives_per_step=collectives, clocks=clk, roofline=roofline,
+        roofline_hbm=roofline_hbm, fp32_peak_tflops=fp32_peak,
+        kernels={k: dict(ms=round(v["ms"], 4), GBps=round(v["GBps"], 1), TFLOPs=round(v["TFLOPs"], 2), bound=v["bound"],
+                         frac=round(v["frac"], 4), per_iter=v["per_iter"], share_of_step=round(v["share_of_step"], 3))
+                 for k, v in kern.items()},
         stats=dict(AverageReturn=algo.sampler.stats.get("AverageReturn"), NumTrajs=algo.sampler.stats.get("NumTrajs")),
+        replicas_identical=replicas_identical, shard_check=shard_check,
+        extra=dict(workloads=extra),
     )
     if env_name in ("swimmer", "hopper") and not args.no_cpu_baseline:
         # the planar-chain oracle is a slow float64 checker (tens of ms per scalar env step), not a CPU implementation
@@ -321,6 +422,7 @@ def main():
         _, info, _ = cpu_arm(args.workload, 2, 1, seconds_budget=args.cpu_seconds)
         line["cpu_baseline"] = info
     print(json.dumps(line))
+    comm.close()
 
 
 if __name__ == "__main__":

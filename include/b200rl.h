@@ -51,9 +51,12 @@ extern "C" {
 
 #define B200RL_LOSS_TRPO 0 /* -mean(exp(logp_new-logp_old)*adv)   rllab/algos/npo.py:72-82 */
 #define B200RL_LOSS_VPG 1  /* -mean(logp*adv)                     rllab/algos/vpg.py:91     */
+#define B200RL_LOSS_KL 2   /* mean KL(old || new): only as the gradient pass of b200rl_update_f64 (FiniteDifferenceHvp) */
 
 #define B200RL_FLAG_DONE 1
 #define B200RL_FLAG_END 2
+#define B200RL_FLAG_CUT 4    /* set with END on a path cut by the end of the lane buffer (neither done nor max length) */
+#define B200RL_FLAG_MASKED 8 /* set by b200rl_process_samples(drop_cut_paths) on every sample of a dropped path */
 
 /* number of float64 slots in the process_samples statistics block (see b200rl_process_samples) */
 #define B200RL_PS_NSUM 16
@@ -63,6 +66,10 @@ const char* b200rl_last_error(void);
 int b200rl_version(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py reports the per-step delta). */
 unsigned long long b200rl_kernel_launches(void);
+/* FP32 roofline microbenchmark (no memory traffic): queues one kernel of num_SMs*8 blocks x 256 threads, each thread
+ * running iters x 16 independent packed fma.rn.f32x2; *fma_out_host = scalar FMAs executed.  The caller times it (CUDA
+ * events) -- bench.py reports the policy passes against this measured FP32 peak. */
+int b200rl_bench_ffma2(int iters, float* sink, long long* fma_out_host, void* stream);
 /* SM count of the current device (grid sizing helper for callers that size workspaces). */
 int b200rl_device_sms(int* sms_out);
 
@@ -116,22 +123,27 @@ int b200rl_rollout(int env_kind, const float* params_f32, int h1, int h2, float 
  *   0 sum adv, 1 sum adv^2, 2 count B, 3 n_paths, 4 sum ret@path start, 5 sum undisc. return, 6 sum undisc^2,
  *   7 sum ret, 8 sum ret^2, 9 sum base, 10 sum base^2, 11 sum (ret-base), 12 sum (ret-base)^2
  * maxs_out [B200RL_PS_NMAX] float64 (all-reduce MAX): 0 max undisc, 1 -min undisc, 2 -min adv, 3 max adv
+ * drop_cut_paths != 0 = the reference's whole_paths=True (batch_polopt.py:30-34: samplers only return whole paths): a
+ * path cut by the end of the lane buffer (B200RL_FLAG_CUT) is dropped -- its samples get B200RL_FLAG_MASKED in `flags`
+ * (in/out), adv = 0, and are left out of every sum above (sums_out[2] is then the number of VALID samples, the divisor
+ * every later pass reads through its `count` argument); 0 keeps the cut path as a truncated path (whole_paths=False,
+ * truncate_paths, parallel_sampler.py:129-155).
  * ws: float64 workspace of at least b200rl_ws_doubles() entries. */
-int b200rl_process_samples(int obs_dim, int N, int T, const float* obs, const float* rew, const unsigned char* flags,
+int b200rl_process_samples(int obs_dim, int N, int T, const float* obs, const float* rew, unsigned char* flags,
                            const unsigned short* tstep, const double* w, double discount, double gae_lambda,
-                           float* adv, float* ret, float* base, double* sums_out, double* maxs_out, double* ws,
-                           void* stream);
+                           int drop_cut_paths, float* adv, float* ret, float* base, double* sums_out, double* maxs_out,
+                           double* ws, void* stream);
 
 /* center_advantages / shift_advantages_to_positive (rllab/algos/util.py:7-12) in place over B samples, from the
- * (already all-reduced) sums/maxs of b200rl_process_samples. */
-int b200rl_center_advantages(float* adv, long long B, const double* sums, const double* maxs, int center,
-                             int positive, void* stream);
+ * (already all-reduced) sums/maxs of b200rl_process_samples; masked samples (flags, may be NULL) keep adv = 0. */
+int b200rl_center_advantages(float* adv, long long B, const unsigned char* flags, const double* sums,
+                             const double* maxs, int center, int positive, void* stream);
 
 /* LinearFeatureBaseline.fit normal equations (linear_feature_baseline.py:26-33): with d = 2O+4 and
  * f = [features, ret], writes gram_out [(d+1)*(d+2)/2] float64 = upper triangle (row-major, i<=j) of sum f f^T
  * over this GPU's samples.  The d x d solve (np.linalg.lstsq on d<=44 unknowns) is done by the caller. */
 int b200rl_lfb_gram(int obs_dim, long long B, const float* obs, const unsigned short* tstep, const float* ret,
-                    double* gram_out, double* ws, void* stream);
+                    const unsigned char* flags, double* gram_out, double* ws, void* stream);
 
 /* The d x d solve of LinearFeatureBaseline.fit on the device (linear_feature_baseline.py:26-37): w_out [d = 2O+4]
  * float64 from gram (b200rl_lfb_gram layout, already all-reduced), regularisation reg_coeff escalated x10 up to 5 times
@@ -141,10 +153,15 @@ int b200rl_lfb_solve(int obs_dim, const double* gram, double reg_coeff, double* 
 
 /* Surrogate loss and KL(old||new) (npo.py:72-82, vpg.py:91-99, diagonal_gaussian.py:14-34,58-69):
  * out[0] = scale * sum(-w*adv) (w = likelihood ratio for TRPO, logp for VPG), out[1] = scale * sum(kl),
- * out[2] = max(kl).  old_log_std [A] (state-independent ParamLayer, lasagne_layers.py:9-30). */
+ * out[2] = max(kl).  old_log_std [A] (state-independent ParamLayer, lasagne_layers.py:9-30).
+ * Common to the update passes: `flags` ([B] or NULL) -- samples carrying B200RL_FLAG_MASKED are skipped; `count` (device
+ * pointer or NULL) -- the sums are additionally divided by *count, the all-reduced number of valid samples
+ * (sums_out[2] of b200rl_process_samples): pass scale = 1 and count = &sums[2] for the mean over the valid samples of
+ * all ranks without reading the count back to the host. */
 int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std,
                    long long B, const float* obs, const float* act, const float* adv, const float* old_mean,
-                   const float* old_log_std, double scale, double* out, double* ws, void* stream);
+                   const float* old_log_std, const unsigned char* flags, double scale, const double* count, double* out,
+                   double* ws, void* stream);
 
 /* Flat gradient of the surrogate (theano.grad in conjugate_gradient_optimizer.py:184-186 /
  * first_order_optimizer.py:62-64): g_out [P] float64 = scale * sum over samples.  loss_out (3 doubles or NULL)
@@ -154,26 +171,37 @@ int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, 
  * ~1 % of the roofline) instead of recomputing two dense layers and 64 tanh per sample. */
 int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std,
                 long long B, const float* obs, const float* act, const float* adv, const float* old_mean,
-                const float* old_log_std, double scale, double* g_out, double* loss_out, float* h_cache_out,
-                double* ws, void* stream);
+                const float* old_log_std, const unsigned char* flags, double scale, const double* count, double* g_out,
+                double* loss_out, float* h_cache_out, double* ws, void* stream);
 
 /* Fisher/Hessian-vector product of mean KL at theta_old (PerlmutterHvp, conjugate_gradient_optimizer.py:22-55):
  * Hx_out [P] = scale * sum_samples J^T M J x  (+ reg_coeff*x and the log_std block added once: pass
  * add_diag=1 on exactly one rank, or on all ranks with diag_scale = 1/world_size).  h_cache: activations written by
- * b200rl_grad at the SAME parameters, or NULL to recompute them. */
+ * b200rl_grad at the SAME parameters, or NULL to recompute them.  tile_list (device int[n_list], or NULL = the whole
+ * batch): indices of the 128-sample tiles to visit -- subsample_factor < 1 of conjugate_gradient_optimizer.py:235-245
+ * at tile granularity (the caller draws the subset and passes count = the number of valid samples in it, see
+ * b200rl_count_valid). */
 int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std, long long B,
-               const float* obs, const double* x, double scale, double reg_coeff, double diag_scale, double* Hx_out,
-               const float* h_cache, double* ws, void* stream);
+               const float* obs, const unsigned char* flags, const double* x, double scale, const double* count,
+               double reg_coeff, double diag_scale, double* Hx_out, const float* h_cache, const int* tile_list,
+               int n_list, double* ws, void* stream);
+
+/* count_out[0] = number of unmasked samples inside the listed 128-sample tiles (tile_list NULL = whole batch). */
+int b200rl_count_valid(long long B, const unsigned char* flags, const int* tile_list, int n_list, double* count_out,
+                       double* ws, void* stream);
 
 /* float64 "parity mode" of the three passes above on the float64 master parameters (mode 0 = loss/KL -> loss_out[3],
  * 1 = gradient -> vec_out[P] (+ loss_out[3] if non-NULL), 2 = Fisher-vector product of x -> vec_out[P]).  The reference's
  * default floatX is float64; with cg_iters = 10 the CG recursion amplifies float32 rounding of the Hessian-vector
  * product past any useful tolerance (DESIGN.md "Parity limit"), so this mode exists to compare the whole TRPO step
- * with the oracle at the reference's default settings.  ~10x slower than the float32 kernels. */
+ * with the oracle at the reference's default settings.  ~10x slower than the float32 kernels.
+ * loss_kind B200RL_LOSS_KL with mode 1 returns the gradient of mean KL(old || new) at params_f64: the two evaluations of
+ * FiniteDifferenceHvp (conjugate_gradient_optimizer.py:58-115), whose 1e-8 relative perturbation needs float64. */
 int b200rl_update_f64(int mode, int loss_kind, const double* params_f64, int obs_dim, int h1, int h2, int act_dim,
                       double min_std, long long B, const float* obs, const float* act, const float* adv,
-                      const float* old_mean, const float* old_log_std, const double* x, double scale, double reg_coeff,
-                      double diag_scale, double* vec_out, double* loss_out, double* ws, void* stream);
+                      const float* old_mean, const float* old_log_std, const unsigned char* flags, const double* x,
+                      double scale, const double* count, double reg_coeff, double diag_scale, double* vec_out,
+                      double* loss_out, double* ws, void* stream);
 
 /* Workspace size (float64 entries) sufficient for every reduction above on the current device. */
 long long b200rl_ws_doubles(void);
@@ -181,10 +209,14 @@ long long b200rl_ws_doubles(void);
 /* ---- P-vector kernels (float64, single block; krylov.cg rllab/misc/krylov.py:7-39 and the step/line-search
  * arithmetic of conjugate_gradient_optimizer.py:258-293; lasagne.updates.adam for VPG) ---- */
 
-/* cg_state [4] float64: 0 rdotr, 1 frozen flag (rdotr < tol seen), 2 last p.z, 3 iterations done */
-int b200rl_cg_init(long long P, const double* g, double* x, double* r, double* p, double* cg_state, void* stream);
+/* cg_state [4] float64: 0 rdotr, 1 frozen flag (rdotr < tol seen), 2 last p.z, 3 iterations done.
+ * p_f32 != 0 keeps the search direction p exactly representable in float32, the precision the float32 Fisher-vector
+ * kernel reads it in, so that z = A p belongs to the very p of the recurrences (krylov.cg run with floatX = float32
+ * stores p in float32 as well). */
+int b200rl_cg_init(long long P, const double* g, double* x, double* r, double* p, double* cg_state, int p_f32,
+                   void* stream);
 int b200rl_cg_step(long long P, const double* z, double* x, double* r, double* p, double* cg_state,
-                   double residual_tol, void* stream);
+                   double residual_tol, int p_f32, void* stream);
 /* step_out [P] = beta * x with beta = sqrt(2*delta/(x.Hx + 1e-8)) (NaN -> 1); info_out[0] = beta */
 int b200rl_trpo_step_size(long long P, const double* x, const double* Hx, double max_constraint_val,
                           double* step_out, double* info_out, void* stream);
@@ -195,6 +227,9 @@ int b200rl_axpy_params(long long P, const double* theta_prev, const double* step
 int b200rl_adam_step(long long P, double* theta, float* theta_f32, const double* g, double* m, double* v,
                      long long t, double lr, double b1, double b2, double eps, void* stream);
 int b200rl_f64_to_f32(long long n, const double* src, float* dst, void* stream);
+/* Local half of the one-collective "mixed all-reduce" of rllab_b200/parallel.py: gathered [world][n] (all-gather of every
+ * rank's vector) -> out[i] = sum over ranks for i < n_sum, max over ranks for i >= n_sum, in rank order. */
+int b200rl_reduce_ranks(const double* gathered, int world, long long n, long long n_sum, double* out, void* stream);
 
 /* (T,N)-planar lane layout <-> the reference's sample-major (B, dim) float64 wire format
  * (samples_data["observations"] etc., rllab/sampler/base.py:74-104): dst[(t*N+n)*dim + k] = src[k][t][n]. */

@@ -24,6 +24,8 @@ from . import policy as P
 
 FLAG_DONE = 1
 FLAG_END = 2
+FLAG_CUT = 4      # with FLAG_END: the path was cut by the end of the lane buffer (neither done nor max_path_length)
+FLAG_MASKED = 8   # device only: set by b200rl_process_samples(drop_cut_paths) on the samples of a dropped path
 
 
 def rollout_lanes(env, theta, dims, N, T, max_path_length, eps, reset_raw, min_std=1e-6,
@@ -52,8 +54,10 @@ def rollout_lanes(env, theta, dims, N, T, max_path_length, eps, reset_raw, min_s
         obs[:, t], act[:, t], mean[:, t], rew[t] = o, a, mu, r
         tstep[t] = plen
         plen = plen + 1
-        end = done | (plen >= max_path_length) | (t == T - 1)
-        flags[t] = done.astype(np.uint8) * FLAG_DONE + end.astype(np.uint8) * FLAG_END
+        whole = done | (plen >= max_path_length)
+        end = whole | (t == T - 1)
+        flags[t] = done.astype(np.uint8) * FLAG_DONE + end.astype(np.uint8) * FLAG_END + \
+            (end & ~whole).astype(np.uint8) * FLAG_CUT
         fresh = env.reset(reset_raw[t + 1]) if reset_states is None else np.array(reset_states[t + 1], dt)
         state = np.where(end[None, :], fresh, state2).astype(dt)
         plen = np.where(end, 0, plen)
@@ -61,7 +65,24 @@ def rollout_lanes(env, theta, dims, N, T, max_path_length, eps, reset_raw, min_s
                 log_std=np.asarray(log_std, dt))
 
 
-def lanes_to_paths(traj):
+def valid_mask(traj, drop_cut=True):
+    """(T, N) bool: samples of whole paths.  A path whose last sample carries FLAG_CUT (cut by the end of the lane
+    buffer) is not a whole path: with whole_paths=True the reference's samplers never return it
+    (batch_polopt.py:30-34; vectorized_sampler.py drops unfinished running_paths)."""
+    fl = np.asarray(traj["flags"])
+    T, N = fl.shape
+    valid = np.ones((T, N), dtype=bool)
+    if not drop_cut:
+        return valid
+    dropped = np.zeros(N, dtype=bool)
+    for t in range(T - 1, -1, -1):
+        e = (fl[t] & FLAG_END) != 0
+        dropped = np.where(e, (fl[t] & FLAG_CUT) != 0, dropped)
+        valid[t] = ~dropped
+    return valid
+
+
+def lanes_to_paths(traj, drop_cut=False):
     """Lane trajectories -> the reference's list-of-path-dicts wire format
     (sampler/utils.py:37-43), lane-major then time order."""
     O, T, N = traj["obs"].shape
@@ -74,6 +95,9 @@ def lanes_to_paths(traj):
             if ends[t, n]:
                 sl = slice(start, t + 1)
                 L = t + 1 - start
+                if drop_cut and (traj["flags"][t, n] & FLAG_CUT):
+                    start = t + 1
+                    continue
                 paths.append(dict(
                     observations=traj["obs"][:, sl, n].T.copy(),
                     actions=traj["act"][:, sl, n].T.copy(),
@@ -114,11 +138,15 @@ def lfb_fit_normal(AtA, Aty, reg_coeff=1e-5):
     return coeffs
 
 
-def lfb_fit_lanes(obs, tstep, ret, reg_coeff=1e-5):
+def lfb_fit_lanes(obs, tstep, ret, reg_coeff=1e-5, valid=None):
     F = lfb_features_lanes(obs, tstep)
     d = F.shape[0]
     Fm = F.reshape(d, -1)
-    return lfb_fit_normal(Fm @ Fm.T, Fm @ np.asarray(ret, np.float64).reshape(-1), reg_coeff)
+    y = np.asarray(ret, np.float64).reshape(-1)
+    if valid is not None:
+        keep = np.asarray(valid).reshape(-1)
+        Fm, y = Fm[:, keep], y[keep]
+    return lfb_fit_normal(Fm @ Fm.T, Fm @ y, reg_coeff)
 
 
 def discount_cumsum(x, discount):
@@ -142,10 +170,11 @@ def explained_variance_1d(ypred, y):
     return 1 - np.var(y - ypred) / (vary + 1e-8)
 
 
-def process_samples_lanes(traj, coeffs, discount, gae_lambda, center_adv=True, positive_adv=False):
+def process_samples_lanes(traj, coeffs, discount, gae_lambda, center_adv=True, positive_adv=False, drop_cut=False):
     """sampler/base.py:48-182 on the lane layout.  `coeffs` = LinearFeatureBaseline weights of the
     previous iteration (None -> zeros, linear_feature_baseline.py:41-42).  Returns dict with
-    adv/ret/base (T,N) and the tabular statistics."""
+    adv/ret/base (T,N) and the tabular statistics.  drop_cut: whole paths only (see valid_mask): the samples of cut
+    paths get adv = 0 and are left out of the centering and of every statistic; `valid` (T,N) is returned."""
     rew = np.asarray(traj["rew"], np.float64)
     T, N = rew.shape
     ends = (traj["flags"] & FLAG_END) != 0
@@ -174,14 +203,18 @@ def process_samples_lanes(traj, coeffs, discount, gae_lambda, center_adv=True, p
         u_next = rew[t] + u_next
         adv[t], ret[t], und[t] = a_next, r_next, u_next
         b_next = base[t]
-    starts = np.asarray(traj["tstep"]) == 0
-    ev = explained_variance_1d(base.reshape(-1), ret.reshape(-1))
-    adv_mean, adv_std = np.mean(adv), np.std(adv)
-    adv_out = adv
+    valid = valid_mask(traj, drop_cut)
+    starts = (np.asarray(traj["tstep"]) == 0) & valid
+    ev = explained_variance_1d(base[valid], ret[valid])
+    adv_mean, adv_std = np.mean(adv[valid]), np.std(adv[valid])
+    adv_v = adv[valid]
     if center_adv:
-        adv_out = (adv_out - np.mean(adv_out)) / (adv_out.std() + 1e-8)     # algos/util.py:7-8
+        adv_v = (adv_v - np.mean(adv_v)) / (adv_v.std() + 1e-8)             # algos/util.py:7-8
     if positive_adv:
-        adv_out = (adv_out - np.min(adv_out)) + 1e-8                        # algos/util.py:11-12
+        adv_v = (adv_v - np.min(adv_v)) + 1e-8                              # algos/util.py:11-12
+    adv_out = np.zeros_like(adv)
+    adv_out[valid] = adv_v
+    adv = np.where(valid, adv, 0.0)
     undisc = und[starts]
     ent = float(P.entropy(np.asarray(traj["log_std"], np.float64)))
     stats = dict(
@@ -196,7 +229,7 @@ def process_samples_lanes(traj, coeffs, discount, gae_lambda, center_adv=True, p
         MinReturn=float(np.min(undisc)),
         adv_mean=float(adv_mean), adv_std=float(adv_std),
     )
-    return dict(adv=adv_out, adv_raw=adv, ret=ret, base=base, stats=stats)
+    return dict(adv=adv_out, adv_raw=adv, ret=ret, base=base, stats=stats, valid=valid)
 
 
 def truncate_paths_lengths(lengths, max_samples):
@@ -214,14 +247,16 @@ def truncate_paths_lengths(lengths, max_samples):
     return lengths
 
 
-def batch_from_traj(traj, adv):
-    """Flatten the lane layout to the (B, .) sample-major layout the oracle losses take."""
+def batch_from_traj(traj, adv, valid=None):
+    """Flatten the lane layout to the (B, .) sample-major layout the oracle losses take; `valid` (T,N) bool keeps the
+    samples of whole paths only."""
     O = traj["obs"].shape[0]
     A = traj["act"].shape[0]
+    keep = slice(None) if valid is None else np.asarray(valid).reshape(-1)
     return dict(
-        obs=np.asarray(traj["obs"], np.float64).reshape(O, -1).T,
-        actions=np.asarray(traj["act"], np.float64).reshape(A, -1).T,
-        adv=np.asarray(adv, np.float64).reshape(-1),
-        old_mean=np.asarray(traj["mean"], np.float64).reshape(A, -1).T,
+        obs=np.asarray(traj["obs"], np.float64).reshape(O, -1).T[keep],
+        actions=np.asarray(traj["act"], np.float64).reshape(A, -1).T[keep],
+        adv=np.asarray(adv, np.float64).reshape(-1)[keep],
+        old_mean=np.asarray(traj["mean"], np.float64).reshape(A, -1).T[keep],
         old_log_std=np.asarray(traj["log_std"], np.float64).reshape(A),
     )

@@ -9,13 +9,13 @@ import os
 from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_uint, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("B200RL_LIB") or os.path.join(_HERE, "csrc", "libb200rl.so")   # B200RL_LIB: A/B builds
+LIB_PATH = os.path.join(_HERE, "csrc", "libb200rl.so")
 
 ENV_POINT, ENV_CARTPOLE, ENV_PENDULUM, ENV_SWIMMER, ENV_HOPPER = 0, 1, 2, 3, 4
 ENV_KINDS = dict(point=ENV_POINT, cartpole=ENV_CARTPOLE, pendulum=ENV_PENDULUM, swimmer=ENV_SWIMMER, hopper=ENV_HOPPER)
 NOISE_UNIFORM, NOISE_NORMAL = 0, 1
-LOSS_TRPO, LOSS_VPG = 0, 1
-FLAG_DONE, FLAG_END = 1, 2
+LOSS_TRPO, LOSS_VPG, LOSS_KL = 0, 1, 2
+FLAG_DONE, FLAG_END, FLAG_CUT, FLAG_MASKED = 1, 2, 4, 8
 PS_NSUM, PS_NMAX = 16, 4
 
 _P = c_void_p
@@ -27,6 +27,7 @@ SIGNATURES = {
     "b200rl_version": (c_int, []),
     "b200rl_kernel_launches": (ctypes.c_ulonglong, []),
     "b200rl_device_sms": (c_int, [POINTER(c_int)]),
+    "b200rl_bench_ffma2": (c_int, [c_int, _P, POINTER(_LL), _P]),
     "b200rl_env_info": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                 POINTER(c_float), POINTER(c_float)]),
     "b200rl_policy_num_params": (_LL, [c_int, c_int, c_int, c_int]),
@@ -37,26 +38,28 @@ SIGNATURES = {
                                           _LL, _P, _P, _P, _P]),
     "b200rl_rollout": (c_int, [c_int, _P, c_int, c_int, c_float, c_int, c_int, c_int, _P, _P, c_uint, c_uint, _LL,
                                _P, _P, _P, _P, _P, _P, _P, _P]),
-    "b200rl_process_samples": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, c_double, c_double, _P, _P, _P, _P, _P,
-                                       _P, _P]),
-    "b200rl_center_advantages": (c_int, [_P, _LL, _P, _P, c_int, c_int, _P]),
-    "b200rl_lfb_gram": (c_int, [c_int, _LL, _P, _P, _P, _P, _P, _P]),
+    "b200rl_process_samples": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, c_double, c_double, c_int, _P, _P, _P,
+                                       _P, _P, _P, _P]),
+    "b200rl_center_advantages": (c_int, [_P, _LL, _P, _P, _P, c_int, c_int, _P]),
+    "b200rl_lfb_gram": (c_int, [c_int, _LL, _P, _P, _P, _P, _P, _P, _P]),
     "b200rl_lfb_solve": (c_int, [c_int, _P, c_double, _P, _P, _P]),
-    "b200rl_loss_kl": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, _P, _P, _P, c_double, _P,
-                               _P, _P]),
-    "b200rl_grad": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, _P, _P, _P, c_double, _P, _P,
-                            _P, _P, _P]),
-    "b200rl_fvp": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, c_double, c_double, c_double, _P, _P,
-                           _P, _P]),
+    "b200rl_loss_kl": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, _P, _P, _P, _P, c_double, _P,
+                               _P, _P, _P]),
+    "b200rl_grad": (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, _P, _P, _P, _P, c_double, _P,
+                            _P, _P, _P, _P, _P]),
+    "b200rl_fvp": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, _LL, _P, _P, _P, c_double, _P, c_double, c_double,
+                           _P, _P, _P, c_int, _P, _P]),
+    "b200rl_count_valid": (c_int, [_LL, _P, _P, c_int, _P, _P, _P]),
     "b200rl_update_f64": (c_int, [c_int, c_int, _P, c_int, c_int, c_int, c_int, c_double, _LL, _P, _P, _P, _P, _P, _P,
-                                  c_double, c_double, c_double, _P, _P, _P, _P]),
+                                  _P, c_double, _P, c_double, c_double, _P, _P, _P, _P]),
     "b200rl_ws_doubles": (_LL, []),
-    "b200rl_cg_init": (c_int, [_LL, _P, _P, _P, _P, _P, _P]),
-    "b200rl_cg_step": (c_int, [_LL, _P, _P, _P, _P, _P, c_double, _P]),
+    "b200rl_cg_init": (c_int, [_LL, _P, _P, _P, _P, _P, c_int, _P]),
+    "b200rl_cg_step": (c_int, [_LL, _P, _P, _P, _P, _P, c_double, c_int, _P]),
     "b200rl_trpo_step_size": (c_int, [_LL, _P, _P, c_double, _P, _P, _P]),
     "b200rl_axpy_params": (c_int, [_LL, _P, _P, c_double, _P, _P, _P]),
     "b200rl_adam_step": (c_int, [_LL, _P, _P, _P, _P, _P, _LL, c_double, c_double, c_double, c_double, _P]),
     "b200rl_f64_to_f32": (c_int, [_LL, _P, _P, _P]),
+    "b200rl_reduce_ranks": (c_int, [_P, c_int, _LL, _LL, _P, _P]),
     "b200rl_planes_to_rows_f64": (c_int, [c_int, _LL, _P, _P, _P]),
 }
 

@@ -63,20 +63,39 @@ class LinearFeatureBaseline(object):
             self._dev_w = torch.as_tensor(np.asarray(self._coeffs, dtype=np.float64)).to(device)
         return self._dev_w
 
-    def fit_lanes(self, batch, comm=None):
+    def gram_lanes(self, batch):
+        """Normal equations A^T A | A^T y of this rank's (unmasked) samples into batch.gram (all-reduced by the sampler
+        together with the advantage statistics)."""
+        from .. import ops
+        ops.lfb_gram(batch, batch.gram)
+
+    def solve_lanes(self, batch):
+        """d x d regularised solve on the device from the all-reduced batch.gram (linear_feature_baseline.py:26-37)."""
         import torch
         from .. import ops
-        d1 = 2 * batch.O + 5
-        if getattr(self, "_gram", None) is None or self._gram.device != batch.device or self._gram.numel() != d1 * (d1 + 1) // 2:
-            self._gram = torch.empty((d1 * (d1 + 1) // 2,), dtype=torch.float64, device=batch.device)
-            self._w_next = torch.empty((d1 - 1,), dtype=torch.float64, device=batch.device)
+        d = 2 * batch.O + 4
+        if getattr(self, "_w_bufs", None) is None or self._w_bufs[0].device != batch.device or self._w_bufs[0].numel() != d:
+            # two weight buffers used alternately: process_samples of the next iteration reads the one solved now
+            self._w_bufs = [torch.zeros((d,), dtype=torch.float64, device=batch.device) for _ in range(2)]
+            self._w_cur = 0
             self._solve_info = torch.zeros((3,), dtype=torch.float64, device=batch.device)
-        ops.lfb_gram(batch, self._gram)
-        if comm is not None:
-            comm.all_reduce_sum(self._gram)
-        ops.lfb_solve(batch.O, self._gram, self._reg_coeff, self._w_next, self._solve_info)
-        self._dev_w = self._w_next.clone()
+        self._w_cur ^= 1
+        w = self._w_bufs[self._w_cur]
+        ops.lfb_solve(batch.O, batch.gram, self._reg_coeff, w, self._solve_info)
+        self._dev_w = w
         self._coeffs = None            # fetched lazily by get_param_values()
+
+    def fit_lanes(self, batch, comm=None):
+        self.gram_lanes(batch)
+        if comm is not None:
+            comm.all_reduce_sum(batch.gram)
+        self.solve_lanes(batch)
+
+    def last_fit_info(self):
+        """(final regularisation, attempts used, ok flag) of the last device solve; ok == 0 means all 5 attempts failed
+        and the weights were set to zero (no baseline) rather than left undefined."""
+        info = getattr(self, "_solve_info", None)
+        return None if info is None else tuple(float(x) for x in info.cpu().numpy())
 
     def __getstate__(self):
         return dict(_coeffs=self.get_param_values(), _reg_coeff=self._reg_coeff)

@@ -21,12 +21,12 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  static int cached[64] = {0};       // per device: a process may drive several GPUs
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cached[dev & 63] > 0) return cached[dev & 63];
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
-  cached = sms;
+  cached[dev & 63] = sms;
   return sms;
 }
 
@@ -70,9 +70,111 @@ int launch_finalize_max(const double* partial, int nblocks, int K, double* out, 
   return 0;
 }
 
+// see common.cuh: blocks [0, ceil(K/32)) reduce the vector, one extra block reduces the loss/KL tuple
+__global__ void __launch_bounds__(256) finalize_update_kernel(FinArgs f) {
+  __shared__ double sm[8][33];
+  const int kx = threadIdx.x & 31, by = threadIdx.x >> 5;
+  const double sc = f.scale / (f.count != nullptr ? f.count[0] : 1.0);
+  const int nvb = (f.K + 31) / 32;
+  if ((int)blockIdx.x < nvb) {
+    const int k = blockIdx.x * 32 + kx;
+    double acc = 0.0;
+    if (k < f.K) {
+#pragma unroll 4
+      for (int b = by; b < f.nblocks; b += 8) acc += f.partial[(size_t)b * f.K + k];
+    }
+    sm[by][kx] = acc;
+    __syncthreads();
+    if (by == 0 && k < f.K) {
+      double r = sm[0][kx];
+#pragma unroll
+      for (int y = 1; y < 8; ++y) r += sm[y][kx];
+      r *= sc;
+      const bool is_ls = (k >= f.ols && k < f.ols + f.A);
+      if (f.post == FIN_GRAD) {
+        // TT.maximum routes the gradient to the constant where the min_std clamp is active (gaussian_mlp_policy.py:100)
+        if (is_ls) {
+          const double par = f.params64 ? f.params64[k] : (double)f.params32[k];
+          if (!(par > f.log_min_std)) r = 0.0;
+        }
+      } else if (f.post == FIN_FVP) {
+        // the log_std slot of the sample sum is zero (the mean does not depend on log_std): reg * x and the M_l block
+        double add = f.reg * f.x[k];
+        if (is_ls) {
+          const double par = f.params64 ? f.params64[k] : (double)f.params32[k];
+          r = 0.0;
+          if (par > f.log_min_std) {
+            const double s = exp(2.0 * par), eps = 1e-8;
+            add += 4.0 * s * (2.0 * s - eps) / ((2.0 * s + eps) * (2.0 * s + eps)) * f.x[k];
+          }
+        }
+        r += f.diag_scale * add;
+      }
+      f.vec_out[k] = r;
+    }
+  } else if (f.tri_out != nullptr) {
+    // tuple: entries [0, NT-1) are sums, entry NT-1 is a max; thread (by, kx): kx < NT handles column kx
+    double acc = (kx == f.NT - 1) ? -1.0e300 : 0.0;
+    if (kx < f.NT) {
+      for (int b = by; b < f.nblocks; b += 8) {
+        const double v = f.tri_partial[(size_t)b * f.NT + kx];
+        acc = (kx == f.NT - 1) ? fmax(acc, v) : acc + v;
+      }
+    }
+    sm[by][kx] = acc;
+    __syncthreads();
+    if (by == 0 && kx < f.NT) {
+      double r = sm[0][kx];
+#pragma unroll
+      for (int y = 1; y < 8; ++y) r = (kx == f.NT - 1) ? fmax(r, sm[y][kx]) : r + sm[y][kx];
+      f.tri_out[kx] = (kx == f.NT - 1) ? r : r * sc;
+    }
+  }
+}
+
+int launch_finalize_update(const FinArgs& f, cudaStream_t s) {
+  const int nvb = (f.K + 31) / 32;
+  finalize_update_kernel<<<nvb + (f.tri_out != nullptr ? 1 : 0), 256, 0, s>>>(f);
+  B200RL_LAUNCH_CHECK("finalize_update_kernel");
+  return 0;
+}
+
+// FP32 issue-rate microbenchmark: 16 independent packed-FMA chains per thread, no memory traffic.  bench.py times it with
+// CUDA events to obtain the FP32 roofline of THIS box (MEASURED_PEAKS.json carries HBM and bf16 tensor peaks only): the
+// policy passes are bound by FP32 / instruction issue, not by HBM.
+__global__ void __launch_bounds__(256) peak_ffma2_kernel(int iters, float seed, float* __restrict__ sink) {
+  float2 acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = make_float2(seed + (float)i, seed - (float)i);
+  const float2 m = make_float2(0.999f, 1.001f), c = make_float2(1e-3f, -1e-3f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+      acc[i] = __ffma2_rn(acc[i], m, c);
+#else
+      acc[i] = make_float2(fmaf(acc[i].x, m.x, c.x), fmaf(acc[i].y, m.y, c.y));
+#endif
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i].x + acc[i].y;
+  if (s == 12345.678f) sink[0] = s;    // never true: keeps the chains alive
+}
+
 }  // namespace b200rl
 
 extern "C" {
+
+int b200rl_bench_ffma2(int iters, float* sink, long long* fma_out, void* stream) {
+  B200RL_REQUIRE(iters > 0 && sink, "bench_ffma2: bad arguments");
+  const int blocks = b200rl::num_sms() * 8;
+  b200rl::peak_ffma2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 1.0f, sink);
+  B200RL_LAUNCH_CHECK("peak_ffma2_kernel");
+  if (fma_out) *fma_out = (long long)blocks * 256 * (long long)iters * 16 * 2;   // scalar FMAs (2 per packed FFMA2)
+  return 0;
+}
 
 const char* b200rl_last_error(void) { return b200rl::g_err; }
 

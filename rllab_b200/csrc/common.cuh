@@ -38,6 +38,20 @@ extern unsigned long long g_kernel_launches;  // every kernel launch of the libr
 
 int num_sms();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE attribute: guard it per (kernel instantiation, device)
+// so that a process that drives several GPUs sets it on each of them (one static mask per call site).
+#define B200RL_SET_MAX_SMEM(kernel, bytes)                                                           \
+  do {                                                                                               \
+    static unsigned long long _done_mask = 0ull;                                                     \
+    int _dev = 0;                                                                                    \
+    B200RL_CUDA_CHECK(cudaGetDevice(&_dev));                                                         \
+    if (!((_done_mask >> (_dev & 63)) & 1ull)) {                                                     \
+      B200RL_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                             (int)(bytes)));                                         \
+      _done_mask |= 1ull << (_dev & 63);                                                             \
+    }                                                                                                \
+  } while (0)
+
 // partial-reduction workspace geometry: every reduction kernel uses at most MAX_PARTIAL_BLOCKS blocks and
 // writes [block][K] float64 partials; K <= MAX_PARTIAL_K.
 constexpr int MAX_PARTIAL_BLOCKS = 148 * 8;
@@ -99,41 +113,19 @@ __device__ __forceinline__ void noise4(int kind, uint32_t seed, uint32_t iter, i
   }
 }
 
-// ---------------------------------------------------------------- experimental: weights through the constant bank
-// Build variant -DB200RL_CONST_WEIGHTS (make VARIANT=cw -> variants/libb200rl_cw.so, select with B200RL_LIB=...): the
-// thread-per-sample kernels read theta from a per-translation-unit __constant__ array, so that the weight operand of
-// every FFMA2 is a uniform-register pair filled by LDCU.128 instead of vector registers filled by LDS.128 (DESIGN.md
-// section 8).  NOT part of the default library: not yet measured on a GPU.
-#ifdef B200RL_CONST_WEIGHTS
-#define B200RL_CONST_MAXP 6144     // >= P of the largest compiled net (Hopper 64x64: 5 702)
-#define B200RL_DEFINE_CONST_THETA                                                                        \
-  __constant__ __align__(16) float c_theta[B200RL_CONST_MAXP];                                           \
-  static int upload_theta(const float* params_dev, int P, cudaStream_t st) {                             \
-    B200RL_REQUIRE(P <= B200RL_CONST_MAXP, "constant-weights variant: too many parameters");             \
-    B200RL_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_theta, params_dev, (size_t)P * sizeof(float), 0,         \
-                                              cudaMemcpyDeviceToDevice, st));                            \
-    return 0;                                                                                            \
-  }
-#endif
-
 // ---------------------------------------------------------------- math
 // tanh used by every kernel (rollout and update MUST share it so that the likelihood ratio is exactly 1 at
-// theta_old): CUDA's tanhf (<= 2 ulp; ~16 instructions with two MUFU ops).  The single definition lives here so that a
-// cheaper variant, if one is ever adopted, replaces it in all kernels at once.
-#ifdef B200RL_FAST_TANH
-// experimental build variant (make VARIANT=ft): 1 - 2 / (2^(2 log2(e) x) + 1) with MUFU.EX2 + MUFU.RCP, 5 instructions
-// instead of tanhf's ~14; saturates correctly (+inf -> 1, 0 -> -1); absolute error <= ~4e-7 (relative accuracy is lost
-// near 0, which the activations do not need).  NumPy emulation: policy mean off by 8e-7 of its scale (tanhf: 7e-8).
-// NOT in the default library: the parity tests have not been run with it on a GPU.
+// theta_old): 1 - 2 / (2^(2 log2(e) x) + 1) with MUFU.EX2 + MUFU.RCP -- 5 instructions instead of tanhf's ~14 (tanhf was
+// 39 % of the rollout's instruction stream); saturates correctly (+inf -> 1, 0 -> -1); absolute error <= ~4e-7 (relative
+// accuracy is lost near 0, which the activations do not need: policy mean off by 8e-7 of its scale against a test
+// tolerance of 2e-5).  A/B on a B200 (round 2, cfg2): rollout 1.45 -> 1.18 ms, loss/KL 1.25 -> 1.04 ms, gradient
+// 3.41 -> 3.23 ms with the full parity suite unchanged.
 __device__ __forceinline__ float tanh_f(float x) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
   return fmaf(-2.0f, r, 1.0f);
 }
-#else
-__device__ __forceinline__ float tanh_f(float x) { return tanhf(x); }
-#endif
 
 // ---------------------------------------------------------------- reductions
 __device__ __forceinline__ double warp_sum(double v) {
@@ -177,5 +169,24 @@ __device__ inline void block_reduce_store(const double (&v)[K], double* scratch,
 // finalize: out[k] = post(sum_b partial[b][k]) in fixed block order; one thread per k.
 int launch_finalize_sum(const double* partial, int nblocks, int K, double* out, double scale, cudaStream_t s);
 int launch_finalize_max(const double* partial, int nblocks, int K, double* out, cudaStream_t s);
+
+// Fused finalize of one policy-update pass (one launch instead of finalize + mask/diag + 2 x finalize + memcpy):
+//   vec_out[k]  = sum_b partial[b][k] * scale / (*count)            k < K            (count == NULL -> 1)
+//   tri_out[0..NT-2] = sum_b tri_partial[b][j] * scale / (*count),  tri_out[NT-1] = max_b tri_partial[b][NT-1]
+//   post == FIN_GRAD : vec_out[ols + a] = 0 where the min_std clamp is active
+//   post == FIN_FVP  : vec_out[p] += diag_scale * (reg * x[p] (+ M_l x_l on un-clamped log_std entries))
+// The count is read from DEVICE memory (the all-reduced number of valid samples, sums[2] of b200rl_process_samples):
+// with whole-path masking the divisor of every mean is only known on the device, and reading it there keeps the
+// iteration free of host synchronisation.
+constexpr int FIN_NONE = 0, FIN_GRAD = 1, FIN_FVP = 2;
+struct FinArgs {
+  const double* partial; int nblocks; int K; double* vec_out;
+  const double* tri_partial; int NT; double* tri_out;
+  double scale; const double* count;
+  int post, ols, A;
+  const float* params32; const double* params64; double log_min_std;
+  const double* x; double reg, diag_scale;
+};
+int launch_finalize_update(const FinArgs& f, cudaStream_t s);
 
 }  // namespace b200rl

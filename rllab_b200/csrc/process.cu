@@ -8,7 +8,6 @@
 
 namespace b200rl {
 
-constexpr int PS_THREADS = 128;
 constexpr int OMAX = 32;  // max obs_dim handled by the runtime-O feature code
 
 // LinearFeatureBaseline features . w  (linear_feature_baseline.py:19-23): [clip(o,+-10), o^2, al, al^2, al^3, 1]
@@ -24,85 +23,165 @@ __device__ __forceinline__ double lfb_predict(const float* __restrict__ obs, siz
   return acc;
 }
 
-// One thread per lane, reverse scan over t.  Recurrences in float64 (the reference runs them in float64).
-__global__ void __launch_bounds__(PS_THREADS)
+// GAE / returns reverse scan, parallel over lanes AND over time (round 2; the one-thread-per-lane walk of round 1 kept
+// only ~14 warps per SM busy at 65 536 lanes and sat at 26 % of the measured HBM bandwidth).
+//
+// A block owns 32 lanes (one warp-width, so every row access is one coalesced 128 B transaction) and walks T backwards
+// in WINDOWS of PS_WARPS x PS_L steps: warp c of the block owns the c-th chunk of PS_L consecutive steps of the window
+// (warp 0 = the latest steps).  The recurrences  x_t = c_t + m_t x_{t+1}  (m_t = factor, or 0 at the last sample of a
+// path) are linear, so each window is resolved with a two-pass chunked scan:
+//   P1  every thread loads its PS_L steps (all loads independent: PS_L x (O+3) in flight per thread), evaluates the
+//       baseline b_t (float64) and publishes the b of its earliest step (the delta of the chunk before it needs it),
+//   P2  local scan with zero carry-in -> values at the chunk's earliest step + "no path end inside the chunk",
+//   P3  every thread folds the aggregates of the later chunks of its lane (<= PS_WARPS-1 three-term updates) into its
+//       true carry-in,
+//   P4  second scan from the registers with the true carry: writes adv / ret, accumulates the statistics.
+// Inputs are read once and outputs written once: HBM traffic = the algorithmic 4*O+19 B per sample.
+// Recurrences and statistics in float64, as the reference runs them (sampler/base.py:57-66, special.py:107-111).
+//
+// drop_cut != 0: a path that carries FLAG_CUT on its last sample (cut by the end of the lane buffer) is dropped, the
+// way the reference's samplers only ever return whole paths (batch_polopt.py:30-34 with whole_paths=True;
+// vectorized_sampler.py drops unfinished running_paths): its samples get FLAG_MASKED, adv = 0, and are excluded from
+// every statistic (count, path counts, returns); downstream kernels skip masked samples.
+constexpr int PS_L = 8, PS_WARPS = 8, PS_THREADS2 = 32 * PS_WARPS, PS_WIN = PS_L * PS_WARPS;
+
+__global__ void __launch_bounds__(PS_THREADS2, 2)
     process_samples_kernel(int O, int N, int T, const float* __restrict__ obs, const float* __restrict__ rew,
-                           const unsigned char* __restrict__ flags, const unsigned short* __restrict__ tstep,
-                           const double* __restrict__ w, double discount, double gl, float* __restrict__ adv,
-                           float* __restrict__ ret, float* __restrict__ base, double* __restrict__ partial_sum,
-                           double* __restrict__ partial_max) {
+                           unsigned char* __restrict__ flags, const unsigned short* __restrict__ tstep,
+                           const double* __restrict__ w, double discount, double gl, int drop_cut,
+                           float* __restrict__ adv, float* __restrict__ ret, float* __restrict__ base,
+                           double* __restrict__ partial_sum, double* __restrict__ partial_max) {
   __shared__ double sw[2 * OMAX + 4];
   __shared__ double scratch[B200RL_PS_NSUM * 32];
+  __shared__ double s_bfirst[PS_WARPS][32];
+  __shared__ double s_agg[PS_WARPS][3][32];
+  __shared__ unsigned char s_st[PS_WARPS][32];     // bit0: no path end inside the chunk, bit1: local "dropped" state
+  __shared__ double s_carry[4][32];                // window carry: adv, ret, undiscounted return, b of the next step
+  __shared__ unsigned char s_mcarry[32];
   const bool have_w = (w != nullptr);
   if (have_w)
     for (int i = threadIdx.x; i < 2 * O + 4; i += blockDim.x) sw[i] = w[i];
+  const int ln = threadIdx.x & 31, c = threadIdx.x >> 5;
+  if (c == 0) {
+    s_carry[0][ln] = 0.0; s_carry[1][ln] = 0.0; s_carry[2][ln] = 0.0; s_carry[3][ln] = 0.0;
+    s_mcarry[ln] = 0;
+  }
   __syncthreads();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.x * 32 + ln;
+  const bool lane_ok = n < N;
+  const size_t plane = (size_t)T * N;
   double s[B200RL_PS_NSUM];
   double m[B200RL_PS_NMAX];
 #pragma unroll
   for (int i = 0; i < B200RL_PS_NSUM; ++i) s[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < B200RL_PS_NMAX; ++i) m[i] = -1.0e300;
-  if (n < N) {
-    const size_t plane = (size_t)T * N;
-    double a_next = 0.0, r_next = 0.0, u_next = 0.0, b_next = 0.0;
-    // The recurrences are sequential in t but the loads are not: fetch CH steps ahead of the arithmetic so that CH
-    // (x up to O+3) independent loads are in flight per thread (the naive loop is long-scoreboard bound, ncu r01b).
-    constexpr int CH = 4;
-    for (int tb = T - 1; tb >= 0; tb -= CH) {
-      unsigned char fl[CH];
-      unsigned short tsv[CH];
-      float rw[CH];
-      double bs[CH];
+  double gl8 = gl * gl, d8 = discount * discount;     // factor ^ PS_L
+  gl8 *= gl8; gl8 *= gl8; d8 *= d8; d8 *= d8;
+  static_assert(PS_L == 8, "the factor powers above assume 8 steps per chunk");
+
+  for (int win_hi = T; win_hi > 0; win_hi -= PS_WIN) {
+    const int t_hi = win_hi - 1 - c * PS_L;            // latest step of this thread's chunk
+    // ---------------- P1: loads + baseline
+    float rw[PS_L];
+    double bs[PS_L];
+    unsigned int endm = 0, startm = 0, cutm = 0;
 #pragma unroll
-      for (int u = 0; u < CH; ++u) {
-        const int t = tb - u;
-        const size_t idx = (size_t)(t >= 0 ? t : 0) * N + n;
-        fl[u] = flags[idx]; tsv[u] = tstep[idx]; rw[u] = rew[idx];
-      }
+    for (int u = 0; u < PS_L; ++u) {
+      const int t = t_hi - u;
+      const bool act = lane_ok && t >= 0;
+      const size_t idx = (size_t)(act ? t : 0) * N + (lane_ok ? n : 0);
+      const unsigned char f = act ? flags[idx] : (unsigned char)0;
+      const unsigned short ts = act ? tstep[idx] : (unsigned short)1;
+      rw[u] = act ? rew[idx] : 0.f;
+      endm |= (unsigned)((f & B200RL_FLAG_END) ? 1 : 0) << u;
+      cutm |= (unsigned)((f & B200RL_FLAG_CUT) ? 1 : 0) << u;
+      startm |= (unsigned)(ts == 0 ? 1 : 0) << u;
+      bs[u] = (have_w && act) ? lfb_predict(obs, plane, idx, O, ts, sw) : 0.0;
+      if (act) base[idx] = (float)bs[u];
+    }
+    if (!drop_cut) cutm = 0;
+    s_bfirst[c][ln] = bs[PS_L - 1];
+    __syncthreads();
+    // ---------------- P2: local scan (zero carry-in)
+    const double b_in = (c == 0) ? s_carry[3][ln] : s_bfirst[c - 1][ln];
+    {
+      double a_n = 0.0, r_n = 0.0, u_n = 0.0, b_n = b_in;
+      bool alive = true, dropped = false;
 #pragma unroll
-      for (int u = 0; u < CH; ++u) {
-        const int t = tb - u;
-        const size_t idx = (size_t)(t >= 0 ? t : 0) * N + n;
-        bs[u] = have_w ? lfb_predict(obs, plane, idx, O, tsv[u], sw) : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < CH; ++u) {
-        const int t = tb - u;
-        if (t < 0) break;
-        const size_t idx = (size_t)t * N + n;
-        const unsigned char f = fl[u];
-        const unsigned short ts = tsv[u];
+      for (int u = 0; u < PS_L; ++u) {
+        if ((endm >> u) & 1u) { a_n = 0.0; r_n = 0.0; u_n = 0.0; b_n = 0.0; alive = false; dropped = (cutm >> u) & 1u; }
         const double r = (double)rw[u];
-        const double b = bs[u];
-        if (f & B200RL_FLAG_END) { a_next = 0.0; r_next = 0.0; u_next = 0.0; b_next = 0.0; }
-        const double delta = r + discount * b_next - b;   // base.py:59-61
-        a_next = delta + gl * a_next;                      // discount_cumsum(deltas, discount*lambda)
-        r_next = r + discount * r_next;                    // discount_cumsum(rewards, discount)
-        u_next = r + u_next;
-        b_next = b;
-        adv[idx] = (float)a_next; ret[idx] = (float)r_next; base[idx] = (float)b;
+        a_n = (r + discount * b_n - bs[u]) + gl * a_n;
+        r_n = r + discount * r_n;
+        u_n = r + u_n;
+        b_n = bs[u];
+      }
+      s_agg[c][0][ln] = a_n; s_agg[c][1][ln] = r_n; s_agg[c][2][ln] = u_n;
+      s_st[c][ln] = (unsigned char)((alive ? 1 : 0) | (dropped ? 2 : 0));
+    }
+    __syncthreads();
+    // ---------------- P3: true carry-in of this chunk
+    double a_n = s_carry[0][ln], r_n = s_carry[1][ln], u_n = s_carry[2][ln];
+    bool dropped = s_mcarry[ln] != 0;
+    for (int cc = 0; cc < c; ++cc) {
+      const unsigned char st = s_st[cc][ln];
+      const bool alive = st & 1;
+      a_n = s_agg[cc][0][ln] + (alive ? gl8 * a_n : 0.0);
+      r_n = s_agg[cc][1][ln] + (alive ? d8 * r_n : 0.0);
+      u_n = s_agg[cc][2][ln] + (alive ? u_n : 0.0);
+      dropped = alive ? dropped : ((st & 2) != 0);
+    }
+    // ---------------- P4: second scan with the true carry, outputs + statistics
+    {
+      double b_n = b_in;
+#pragma unroll
+      for (int u = 0; u < PS_L; ++u) {
+        const int t = t_hi - u;
+        if (!(lane_ok && t >= 0)) continue;
+        const size_t idx = (size_t)t * N + n;
+        if ((endm >> u) & 1u) { a_n = 0.0; r_n = 0.0; u_n = 0.0; b_n = 0.0; dropped = (cutm >> u) & 1u; }
+        const double r = (double)rw[u], b = bs[u];
+        a_n = (r + discount * b_n - b) + gl * a_n;          // base.py:59-61, discount_cumsum(deltas, discount*lambda)
+        r_n = r + discount * r_n;                            // discount_cumsum(rewards, discount)
+        u_n = r + u_n;
+        b_n = b;
+        ret[idx] = (float)r_n;
+        if (dropped) {
+          adv[idx] = 0.f;
+          flags[idx] = (unsigned char)(((endm >> u) & 1u ? B200RL_FLAG_END : 0) | ((cutm >> u) & 1u ? B200RL_FLAG_CUT : 0) |
+                                       B200RL_FLAG_MASKED | (flags[idx] & B200RL_FLAG_DONE));
+          continue;
+        }
+        adv[idx] = (float)a_n;
         // statistics use the float64 values (as the reference does)
-        s[0] += a_next; s[1] += a_next * a_next; s[2] += 1.0;
-        s[7] += r_next; s[8] += r_next * r_next; s[9] += b; s[10] += b * b;
-        const double res = r_next - b;
+        s[0] += a_n; s[1] += a_n * a_n; s[2] += 1.0;
+        s[7] += r_n; s[8] += r_n * r_n; s[9] += b; s[10] += b * b;
+        const double res = r_n - b;
         s[11] += res; s[12] += res * res;
-        m[2] = fmax(m[2], -a_next); m[3] = fmax(m[3], a_next);
-        if (ts == 0) {  // first sample of a path
-          s[3] += 1.0; s[4] += r_next; s[5] += u_next; s[6] += u_next * u_next;
-          m[0] = fmax(m[0], u_next); m[1] = fmax(m[1], -u_next);
+        m[2] = fmax(m[2], -a_n); m[3] = fmax(m[3], a_n);
+        if ((startm >> u) & 1u) {  // first sample of a path
+          s[3] += 1.0; s[4] += r_n; s[5] += u_n; s[6] += u_n * u_n;
+          m[0] = fmax(m[0], u_n); m[1] = fmax(m[1], -u_n);
         }
       }
     }
+    // window carry-out: the chunk that holds the earliest steps of the window (read again only after the next
+    // window's first barrier)
+    if (c == PS_WARPS - 1) {
+      s_carry[0][ln] = a_n; s_carry[1][ln] = r_n; s_carry[2][ln] = u_n; s_carry[3][ln] = bs[PS_L - 1];
+      s_mcarry[ln] = dropped ? 1 : 0;
+    }
   }
+  __syncthreads();
   block_reduce_store<B200RL_PS_NSUM, false>(s, scratch, partial_sum + (size_t)blockIdx.x * B200RL_PS_NSUM);
   block_reduce_store<B200RL_PS_NMAX, true>(m, scratch, partial_max + (size_t)blockIdx.x * B200RL_PS_NMAX);
 }
 
 // (adv - mean) / (std + 1e-8), then optionally (adv - min) + 1e-8   (algos/util.py:7-12)
-__global__ void center_adv_kernel(float* __restrict__ adv, long long B, const double* __restrict__ sums,
-                                  const double* __restrict__ maxs, int center, int positive) {
+__global__ void center_adv_kernel(float* __restrict__ adv, long long B, const unsigned char* __restrict__ flags,
+                                  const double* __restrict__ sums, const double* __restrict__ maxs, int center,
+                                  int positive) {
   const double cnt = sums[2];
   const double mean = sums[0] / cnt;
   double var = sums[1] / cnt - mean * mean;
@@ -112,6 +191,7 @@ __global__ void center_adv_kernel(float* __restrict__ adv, long long B, const do
   if (center) mn = (mn - mean) / stdv;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) {
+    if (flags != nullptr && (flags[i] & B200RL_FLAG_MASKED)) continue;   // dropped path: adv stays 0
     double a = (double)adv[i];
     if (center) a = (a - mean) / stdv;
     if (positive) a = (a - mn) + 1e-8;
@@ -129,7 +209,8 @@ constexpr int GRAM_MAXPAIRS_PER_THREAD = 9;  // (2*20+5)*(2*20+6)/2 = 1035 pairs
 
 __global__ void __launch_bounds__(GRAM_THREADS)
     lfb_gram_kernel(int O, long long B, const float* __restrict__ obs, const unsigned short* __restrict__ tstep,
-                    const float* __restrict__ ret, double* __restrict__ partial) {
+                    const float* __restrict__ ret, const unsigned char* __restrict__ flags,
+                    double* __restrict__ partial) {
   extern __shared__ __align__(16) float F[];  // [(d+1)][GRAM_LD]
   const int d1 = 2 * O + 5;
   const int npairs = d1 * (d1 + 1) / 2;
@@ -152,7 +233,7 @@ __global__ void __launch_bounds__(GRAM_THREADS)
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long sidx = tile * GRAM_TILE + threadIdx.x;
     __syncthreads();
-    if (sidx < B) {
+    if (sidx < B && !(flags != nullptr && (flags[sidx] & B200RL_FLAG_MASKED))) {
       for (int k = 0; k < O; ++k) {
         float o = fminf(fmaxf(obs[(size_t)k * B + sidx], -10.0f), 10.0f);
         F[k * GRAM_LD + threadIdx.x] = o;
@@ -197,7 +278,9 @@ __global__ void __launch_bounds__(GRAM_THREADS)
 template <int O>
 __global__ void __launch_bounds__(128) lfb_gram_reg_kernel(long long B, const float* __restrict__ obs,
                                                            const unsigned short* __restrict__ tstep,
-                                                           const float* __restrict__ ret, double* __restrict__ partial) {
+                                                           const float* __restrict__ ret,
+                                                           const unsigned char* __restrict__ flags,
+                                                           double* __restrict__ partial) {
   constexpr int D1 = 2 * O + 5, NP = D1 * (D1 + 1) / 2;
   __shared__ double red[NP];
   float acc[NP];
@@ -209,11 +292,13 @@ __global__ void __launch_bounds__(128) lfb_gram_reg_kernel(long long B, const fl
   constexpr int UNR = 4;   // 4 samples' loads in flight per thread (memory-level parallelism; one is latency bound)
   for (long long s0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; s0 < B; s0 += UNR * stride) {
     float raw[UNR][O + 2];
+    bool use[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const long long s = s0 + u * stride;
       const bool ok = s < B;
       const long long sl = ok ? s : s0;
+      use[u] = ok && !(flags != nullptr && (flags[sl] & B200RL_FLAG_MASKED));
 #pragma unroll
       for (int k = 0; k < O; ++k) raw[u][k] = obs[(size_t)k * B + sl];
       raw[u][O] = (float)tstep[sl];
@@ -221,7 +306,7 @@ __global__ void __launch_bounds__(128) lfb_gram_reg_kernel(long long B, const fl
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      if (s0 + u * stride < B) {
+      if (use[u]) {
         float f[D1];
 #pragma unroll
         for (int k = 0; k < O; ++k) {
@@ -266,42 +351,43 @@ using namespace b200rl;
 
 extern "C" {
 
-int b200rl_process_samples(int obs_dim, int N, int T, const float* obs, const float* rew, const unsigned char* flags,
+int b200rl_process_samples(int obs_dim, int N, int T, const float* obs, const float* rew, unsigned char* flags,
                            const unsigned short* tstep, const double* w, double discount, double gae_lambda,
-                           float* adv, float* ret, float* base, double* sums_out, double* maxs_out, double* ws,
-                           void* stream) {
+                           int drop_cut_paths, float* adv, float* ret, float* base, double* sums_out, double* maxs_out,
+                           double* ws, void* stream) {
   B200RL_REQUIRE(obs && rew && flags && tstep && adv && ret && base && sums_out && maxs_out && ws,
                  "process_samples: null buffer");
   B200RL_REQUIRE(N > 0 && T > 0 && obs_dim > 0 && obs_dim <= OMAX, "process_samples: bad sizes");
-  const int grid = (N + PS_THREADS - 1) / PS_THREADS;
-  // lanes beyond the partial-block budget: use a wider block instead of more blocks
-  B200RL_REQUIRE(grid <= 65536, "process_samples: too many lanes for one call (N <= 8M)");
+  const int grid = (N + 31) / 32;          // one block per 32 lanes (PS_WARPS warps walk T in windows)
+  B200RL_REQUIRE(grid <= 262144, "process_samples: too many lanes for one call (N <= 8M)");
   cudaStream_t st = (cudaStream_t)stream;
   double* psum = ws;
   double* pmax = ws + (size_t)grid * B200RL_PS_NSUM;
   B200RL_REQUIRE((long long)grid * (B200RL_PS_NSUM + B200RL_PS_NMAX) <= b200rl_ws_doubles(), "workspace too small");
-  process_samples_kernel<<<grid, PS_THREADS, 0, st>>>(obs_dim, N, T, obs, rew, flags, tstep, w, discount,
-                                                      discount * gae_lambda, adv, ret, base, psum, pmax);
+  process_samples_kernel<<<grid, PS_THREADS2, 0, st>>>(obs_dim, N, T, obs, rew, flags, tstep, w, discount,
+                                                       discount * gae_lambda, drop_cut_paths, adv, ret, base, psum,
+                                                       pmax);
   B200RL_LAUNCH_CHECK("process_samples_kernel");
   int rc = launch_finalize_sum(psum, grid, B200RL_PS_NSUM, sums_out, 1.0, st);
   if (rc) return rc;
   return launch_finalize_max(pmax, grid, B200RL_PS_NMAX, maxs_out, st);
 }
 
-int b200rl_center_advantages(float* adv, long long B, const double* sums, const double* maxs, int center,
-                             int positive, void* stream) {
+int b200rl_center_advantages(float* adv, long long B, const unsigned char* flags, const double* sums,
+                             const double* maxs, int center, int positive, void* stream) {
   B200RL_REQUIRE(adv && sums && maxs && B > 0, "center_advantages: bad arguments");
   if (!center && !positive) return 0;
   long long blocks = (B + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  center_adv_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(adv, B, sums, maxs, center, positive);
+  center_adv_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(adv, B, flags, sums, maxs, center,
+                                                                         positive);
   B200RL_LAUNCH_CHECK("center_adv_kernel");
   return 0;
 }
 
 int b200rl_lfb_gram(int obs_dim, long long B, const float* obs, const unsigned short* tstep, const float* ret,
-                    double* gram_out, double* ws, void* stream) {
+                    const unsigned char* flags, double* gram_out, double* ws, void* stream) {
   B200RL_REQUIRE(obs && tstep && ret && gram_out && ws && B > 0, "lfb_gram: bad arguments");
   B200RL_REQUIRE(obs_dim > 0 && obs_dim <= 20, "lfb_gram: obs_dim must be in 1..20");
   const int d1 = 2 * obs_dim + 5;
@@ -318,15 +404,16 @@ int b200rl_lfb_gram(int obs_dim, long long B, const float* obs, const unsigned s
     if (g > need) g = need;
     grid = (int)g;
     switch (obs_dim) {
-      case 1: lfb_gram_reg_kernel<1><<<grid, 128, 0, st>>>(B, obs, tstep, ret, ws); break;
-      case 2: lfb_gram_reg_kernel<2><<<grid, 128, 0, st>>>(B, obs, tstep, ret, ws); break;
-      case 3: lfb_gram_reg_kernel<3><<<grid, 128, 0, st>>>(B, obs, tstep, ret, ws); break;
-      default: lfb_gram_reg_kernel<4><<<grid, 128, 0, st>>>(B, obs, tstep, ret, ws); break;
+      case 1: lfb_gram_reg_kernel<1><<<grid, 128, 0, st>>>(B, obs, tstep, ret, flags, ws); break;
+      case 2: lfb_gram_reg_kernel<2><<<grid, 128, 0, st>>>(B, obs, tstep, ret, flags, ws); break;
+      case 3: lfb_gram_reg_kernel<3><<<grid, 128, 0, st>>>(B, obs, tstep, ret, flags, ws); break;
+      default: lfb_gram_reg_kernel<4><<<grid, 128, 0, st>>>(B, obs, tstep, ret, flags, ws); break;
     }
     B200RL_LAUNCH_CHECK("lfb_gram_reg_kernel");
     return launch_finalize_sum(ws, grid, npairs, gram_out, 1.0, st);
   }
-  lfb_gram_kernel<<<grid, GRAM_THREADS, smem, st>>>(obs_dim, B, obs, tstep, ret, ws);
+  B200RL_SET_MAX_SMEM(lfb_gram_kernel, smem);
+  lfb_gram_kernel<<<grid, GRAM_THREADS, smem, st>>>(obs_dim, B, obs, tstep, ret, flags, ws);
   B200RL_LAUNCH_CHECK("lfb_gram_kernel");
   return launch_finalize_sum(ws, grid, npairs, gram_out, 1.0, st);
 }

@@ -64,26 +64,33 @@ struct RolloutArgs {
   float* log_std_out;
 };
 
-#ifdef B200RL_CONST_WEIGHTS
-B200RL_DEFINE_CONST_THETA
-#endif
+// Policy weights of the 32-wide rollout through the CONSTANT bank: with theta in a __constant__ array the dense layers
+// compile to `LDCU.128 UR, c[...]` (uniform datapath, one load per warp) + `FFMA2 R, R.F32, UR.F32x2, R` -- the weight
+// pair is a uniform-register operand -- instead of LDS.128 + vector registers (the fully unrolled 32-wide layers index
+// the weights with compile-time offsets).  A/B on a B200 (round 2, cfg2, together with the 5-instruction tanh): rollout
+// 1.18 -> 1.00 ms, 92 registers.  The same change LOSES in the thread-per-sample update kernels (tile gradient 3.2 ->
+// 4.4 ms: its staging wants the registers), which therefore keep theta in shared memory.  theta is refreshed by one
+// stream-ordered device-to-device cudaMemcpyToSymbolAsync (<= 7 KB) per rollout.
+constexpr int ROLLOUT_CONST_MAXP = 2048;     // >= P of the largest 32-wide net (Hopper obs 20: 1 830)
+__constant__ __align__(16) float c_theta[ROLLOUT_CONST_MAXP];
+template <int H>
+constexpr bool rollout_const_weights() { return H == 32; }
 
 // One thread per lane; the whole T-step trajectory of a lane stays in that thread's registers.
 template <class Env, int H>
 __global__ void __launch_bounds__(ROLLOUT_THREADS, rollout_minblocks<Env, H>()) rollout_kernel(RolloutArgs a) {
   using N_ = Net<Env::O, H, H, Env::A>;
-  // 32-wide: parameters only (static); 64-wide: + one activation column per thread for the rolled layer-2 loop
+  // 32-wide: parameters in the constant bank; 64-wide: parameters in shared memory + one activation column per thread
+  // for the rolled layer-2 loop
   constexpr int P4 = (N_::P + 3) & ~3;
+  constexpr bool CW = rollout_const_weights<H>();
   extern __shared__ __align__(16) float rollout_smem[];
-#ifdef B200RL_CONST_WEIGHTS
-  const float* sp = c_theta;
+  const float* sp = CW ? c_theta : rollout_smem;
   float* hcol = (H > 32) ? rollout_smem + P4 + threadIdx.x : nullptr;
-#else
-  float* sp = rollout_smem;
-  float* hcol = (H > 32) ? rollout_smem + P4 + threadIdx.x : nullptr;
-  for (int i = threadIdx.x; i < N_::P; i += blockDim.x) sp[i] = a.params[i];
-  __syncthreads();
-#endif
+  if constexpr (!CW) {
+    for (int i = threadIdx.x; i < N_::P; i += blockDim.x) rollout_smem[i] = a.params[i];
+    __syncthreads();
+  }
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   float std_[Env::A];
 #pragma unroll
@@ -121,9 +128,13 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, rollout_minblocks<Env, H>()) 
     Env::step(s, u, r, done);
     a.tstep[idx] = (unsigned short)plen;
     ++plen;
-    const bool end = done || (plen >= a.max_path_length) || (t == a.T - 1);
+    const bool whole = done || (plen >= a.max_path_length);
+    const bool end = whole || (t == a.T - 1);
     a.rew[idx] = r;
-    a.flags[idx] = (unsigned char)((done ? B200RL_FLAG_DONE : 0) | (end ? B200RL_FLAG_END : 0));
+    // FLAG_CUT: the path is cut by the end of the lane buffer, not by the env or max_path_length (process_samples drops
+    // such paths when the caller asks for whole paths only, batch_polopt.py:30-34)
+    a.flags[idx] = (unsigned char)((done ? B200RL_FLAG_DONE : 0) | (end ? B200RL_FLAG_END : 0) |
+                                   ((end && !whole) ? B200RL_FLAG_CUT : 0));
     if (end) {
       draw_reset<Env>(s, a.reset_raw, t + 1, a.N, n, a.seed, a.iter, lane);
       plen = 0;
@@ -226,24 +237,16 @@ __global__ void fill_noise_kernel(float* __restrict__ out, int rows, int row0, i
 template <class Env>
 static int launch_rollout(int h, const RolloutArgs& a, cudaStream_t st) {
   const int grid = (a.N + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
-#ifdef B200RL_CONST_WEIGHTS
-  if (h == 32 || h == 64) {
-    int rc = upload_theta(a.params, h == 32 ? Net<Env::O, 32, 32, Env::A>::P : Net<Env::O, 64, 64, Env::A>::P, st);
-    if (rc) return rc;
-  }
-#endif
   if (h == 32) {
     using N32 = Net<Env::O, 32, 32, Env::A>;
-    rollout_kernel<Env, 32><<<grid, ROLLOUT_THREADS, ((N32::P + 3) & ~3) * sizeof(float), st>>>(a);
+    static_assert(N32::P <= ROLLOUT_CONST_MAXP, "constant bank too small for this net");
+    B200RL_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_theta, a.params, (size_t)N32::P * sizeof(float), 0,
+                                              cudaMemcpyDeviceToDevice, st));
+    rollout_kernel<Env, 32><<<grid, ROLLOUT_THREADS, 0, st>>>(a);
   } else if (h == 64) {
     using N64 = Net<Env::O, 64, 64, Env::A>;
     const size_t smem = (((N64::P + 3) & ~3) + 64 * ROLLOUT_THREADS) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-      B200RL_CUDA_CHECK(cudaFuncSetAttribute(rollout_kernel<Env, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-      attr_done = true;
-    }
+    B200RL_SET_MAX_SMEM((rollout_kernel<Env, 64>), smem);
     rollout_kernel<Env, 64><<<grid, ROLLOUT_THREADS, smem, st>>>(a);
   } else {
     set_error("hidden size %d not compiled in (32 or 64)", h);

@@ -17,8 +17,8 @@ struct TileDist {  // per-kernel distribution constants (A <= 3)
 
 template <class N, int MODE, class SM, int LD>
 __device__ __forceinline__ void tile_phase_a(const UpdArgs& a, const float* sp, const float* sv, float* stage,
-                                             const TileDist& D, long long sl, bool valid, int tid, double& s_loss,
-                                             double& s_kl, double& m_kl) {
+                                             const TileDist& D, long long sl, bool inrange, bool valid, int tid,
+                                             double& s_loss, double& s_kl, double& m_kl) {
   constexpr int O = N::O, H = 32, A = N::A;
   float* colX = stage + SM::rX * LD + tid;
   float* colH1 = stage + SM::rH1 * LD + tid;
@@ -67,7 +67,7 @@ __device__ __forceinline__ void tile_phase_a(const UpdArgs& a, const float* sp, 
     }
 #pragma unroll
     for (int j = 0; j < H; ++j) colH2[j * LD] = h2[j];
-    if (MODE == MODE_GRAD && hc != nullptr && valid) {
+    if (MODE == MODE_GRAD && hc != nullptr && inrange) {   // masked samples too: the FVP pass reads their rows back
 #pragma unroll
       for (int j = 0; j < H; ++j) {
         hc[(size_t)j * a.B] = colH1[j * LD];

@@ -1,5 +1,5 @@
-// Shared declarations of the policy-update kernels (update.cu: warp-per-sample, 64-wide nets; update_tile.cu:
-// thread-per-sample + shared-memory Gram accumulation, 32-wide nets).
+// Shared declarations of the policy-update kernels (update.cu: loss/KL pass + the C entry points; update_tile.cu:
+// thread-per-sample + shared-memory Gram accumulation, 32-wide nets; update_gemm.cu: tiled-GEMM formulation, 64-wide nets).
 #pragma once
 #include "mlp.cuh"
 
@@ -15,9 +15,26 @@ struct UpdArgs {
   long long B;
   const float *obs, *act, *adv, *old_mean, *old_log_std;
   int loss_kind;
-  int unit_half;  // 64-wide nets: which half of the layer-2 units accumulates dW1 in this pass (0/1)
+  const unsigned char* flags;  // [B] or NULL: samples carrying B200RL_FLAG_MASKED contribute nothing
+  const int* tile_list;        // FVP sub-sampling: indices of the 128-sample tiles to visit (device), or NULL = all tiles
+  int n_list;
   double* partial;
 };
+
+// valid sample: inside the batch and not masked out by process_samples(drop_cut_paths)
+__device__ __forceinline__ bool sample_valid(const UpdArgs& a, long long s) {
+  return s < a.B && !(a.flags != nullptr && (a.flags[s] & B200RL_FLAG_MASKED));
+}
+// number of tiles a kernel iterates over and the i-th of them
+__device__ __forceinline__ long long n_tiles_of(const UpdArgs& a, int tile) {
+  return a.tile_list != nullptr ? (long long)a.n_list : (a.B + tile - 1) / tile;
+}
+__device__ __forceinline__ long long tile_at(const UpdArgs& a, long long i) {
+  return a.tile_list != nullptr ? (long long)a.tile_list[i] : i;
+}
+inline long long host_n_tiles(const UpdArgs& a, int tile) {
+  return a.tile_list != nullptr ? (long long)a.n_list : (a.B + tile - 1) / tile;
+}
 
 // 32-wide nets.  Launches the tile kernel on `a` (a.partial = workspace); returns the grid size used (blocks that
 // wrote partial[block][P] (+ [grid][3] loss scalars after them in MODE_GRAD)), P and the log_std offset.
@@ -28,8 +45,5 @@ int update_tile_launch(int mode, int obs_dim, int act_dim, const UpdArgs& a, int
 int update_gemm_launch(int mode, int obs_dim, int h, int act_dim, const UpdArgs& a, int* grid_out, int* P_out,
                        int* ols_out, cudaStream_t st);
 
-// which implementation b200rl_grad / b200rl_fvp use: env B200RL_UPDATE_IMPL = auto (default: tile for 32-wide, gemm for
-// 64-wide nets) | gemm | tile | warp
-int update_impl();
 
 }  // namespace b200rl

@@ -22,6 +22,7 @@ struct UpdArgs64 {
   long long B;
   const float *obs, *act, *adv, *old_mean, *old_log_std;
   int loss_kind;
+  const unsigned char* flags;
   double* partial;
 };
 
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(D_THREADS) update_f64_kernel(UpdArgs64 a) {
   double s_loss = 0.0, s_kl = 0.0, m_kl = -1.0e300;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < a.B; s += stride) {
+    if (a.flags != nullptr && (a.flags[s] & B200RL_FLAG_MASKED)) continue;      // sample of a dropped (cut) path
     double x[O], h1[H1], h2[H2], mu[A], dmu[A], dls[A];
 #pragma unroll
     for (int o = 0; o < O; ++o) x[o] = (double)a.obs[(size_t)o * a.B + s];
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(D_THREADS) update_f64_kernel(UpdArgs64 a) {
         for (int j = 0; j < H2; ++j) m = fma(h2[j], sp[N::oWo + j * A + k], m);
         mu[k] = m;
       }
-      double zsq = 0.0, zsq_old = 0.0, kl = 0.0, z[A];
+      double zsq = 0.0, zsq_old = 0.0, kl = 0.0, z[A], dkl_mu[A], dkl_ls[A];
 #pragma unroll
       for (int k = 0; k < A; ++k) {
         const double act = (double)a.act[(size_t)k * a.B + s], om = (double)a.old_mean[(size_t)k * a.B + s];
@@ -92,8 +94,11 @@ __global__ void __launch_bounds__(D_THREADS) update_f64_kernel(UpdArgs64 a) {
         const double zo = (act - om) / sd_old[k];
         zsq_old += zo * zo;
         const double dm = om - mu[k];
-        kl += (dm * dm + sd_old[k] * sd_old[k] - sd_new[k] * sd_new[k]) / (2.0 * sd_new[k] * sd_new[k] + 1e-8) +
-              ls_new[k] - ls_old[k];
+        const double sn = sd_new[k] * sd_new[k], so = sd_old[k] * sd_old[k], den = 2.0 * sn + 1e-8;
+        kl += (dm * dm + so - sn) / den + ls_new[k] - ls_old[k];
+        // d kl / d mu_new and d kl / d log_std_new (diagonal_gaussian.py:14-34), used by the B200RL_LOSS_KL gradient
+        dkl_mu[k] = -2.0 * dm / den;
+        dkl_ls[k] = 1.0 - (2.0 * sn * den + 4.0 * sn * (dm * dm + so - sn)) / (den * den);
       }
       const double adv_s = (double)a.adv[s];
       const double logp_new = -sum_ls_new - 0.5 * zsq - half_log2pi_A;
@@ -112,8 +117,13 @@ __global__ void __launch_bounds__(D_THREADS) update_f64_kernel(UpdArgs64 a) {
       if (MODE == MODE_LOSS) continue;
 #pragma unroll
       for (int k = 0; k < A; ++k) {
-        dmu[k] = -w_s * z[k] / sd_new[k];
-        dls[k] = -w_s * (z[k] * z[k] - 1.0);
+        if (a.loss_kind == B200RL_LOSS_KL) {          // gradient of mean KL(old || new) (FiniteDifferenceHvp)
+          dmu[k] = dkl_mu[k];
+          dls[k] = dkl_ls[k];
+        } else {
+          dmu[k] = -w_s * z[k] / sd_new[k];
+          dls[k] = -w_s * (z[k] * z[k] - 1.0);
+        }
       }
     } else {
       // tangent forward
@@ -190,12 +200,7 @@ __global__ void __launch_bounds__(D_THREADS) update_f64_kernel(UpdArgs64 a) {
 template <class N, int MODE>
 static int launch_f64(const UpdArgs64& a, int* grid_out, cudaStream_t st) {
   const size_t smem = (size_t)3 * N::P * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    B200RL_CUDA_CHECK(cudaFuncSetAttribute(update_f64_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
-    attr_done = true;
-  }
+  B200RL_SET_MAX_SMEM((update_f64_kernel<N, MODE>), smem);
   long long grid = (long long)num_sms() * 2;
   const long long need = (a.B + D_THREADS - 1) / D_THREADS;
   if (grid > need) grid = need;
@@ -203,27 +208,6 @@ static int launch_f64(const UpdArgs64& a, int* grid_out, cudaStream_t st) {
   B200RL_LAUNCH_CHECK("update_f64_kernel");
   *grid_out = (int)grid;
   return 0;
-}
-
-__global__ void fvp_diag_f64_kernel(int P, int ols, int A, const double* __restrict__ params, double log_min_std,
-                                    const double* __restrict__ x, double reg, double diag_scale, double* __restrict__ Hx) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  double add = reg * x[p];
-  if (p >= ols && p < ols + A) {
-    if (params[p] > log_min_std) {
-      const double s = exp(2.0 * params[p]);
-      const double eps = 1e-8;
-      add += 4.0 * s * (2.0 * s - eps) / ((2.0 * s + eps) * (2.0 * s + eps)) * x[p];
-    }
-  }
-  Hx[p] = (p >= ols && p < ols + A ? 0.0 : Hx[p]) + diag_scale * add;
-}
-
-__global__ void mask_logstd_grad_f64_kernel(int ols, int A, const double* __restrict__ params, double log_min_std,
-                                            double* __restrict__ g) {
-  const int k = threadIdx.x;
-  if (k < A && !(params[ols + k] > log_min_std)) g[ols + k] = 0.0;
 }
 
 }  // namespace b200rl
@@ -234,18 +218,21 @@ extern "C" {
 
 int b200rl_update_f64(int mode, int loss_kind, const double* params_f64, int obs_dim, int h1, int h2, int act_dim,
                       double min_std, long long B, const float* obs, const float* act, const float* adv,
-                      const float* old_mean, const float* old_log_std, const double* x, double scale, double reg_coeff,
-                      double diag_scale, double* vec_out, double* loss_out, double* ws, void* stream) {
+                      const float* old_mean, const float* old_log_std, const unsigned char* flags, const double* x,
+                      double scale, const double* count, double reg_coeff, double diag_scale, double* vec_out,
+                      double* loss_out, double* ws, void* stream) {
   B200RL_REQUIRE(params_f64 && obs && ws && B > 0, "update_f64: bad arguments");
   B200RL_REQUIRE(mode == MODE_LOSS || mode == MODE_GRAD || mode == MODE_FVP, "update_f64: bad mode");
   B200RL_REQUIRE(mode == MODE_FVP ? (x && vec_out) : (act && adv && old_mean && old_log_std), "update_f64: null buffer");
   B200RL_REQUIRE(mode != MODE_GRAD || vec_out, "update_f64: gradient output missing");
   B200RL_REQUIRE(mode != MODE_LOSS || loss_out, "update_f64: loss output missing");
+  B200RL_REQUIRE(loss_kind == B200RL_LOSS_TRPO || loss_kind == B200RL_LOSS_VPG ||
+                 (loss_kind == B200RL_LOSS_KL && mode == MODE_GRAD), "update_f64: bad loss kind");
   cudaStream_t st = (cudaStream_t)stream;
   UpdArgs64 a{};
   a.params = params_f64; a.xvec = x; a.log_min_std = min_std > 0.0 ? log(min_std) : -INFINITY; a.B = B;
   a.obs = obs; a.act = act; a.adv = adv; a.old_mean = old_mean; a.old_log_std = old_log_std;
-  a.loss_kind = loss_kind; a.partial = ws;
+  a.loss_kind = loss_kind; a.flags = flags; a.partial = ws;
   int grid = 0, P = 0, ols = 0;
   B200RL_DISPATCH_NET({
     P = NetT::P; ols = NetT::ols;
@@ -254,27 +241,16 @@ int b200rl_update_f64(int mode, int loss_kind, const double* params_f64, int obs
                                  : launch_f64<NetT, MODE_FVP>(a, &grid, st);
     if (rc) return rc;
   });
-  if (mode != MODE_LOSS) {
-    int rc = launch_finalize_sum(ws, grid, P, vec_out, scale, st);
-    if (rc) return rc;
-    if (mode == MODE_GRAD) {
-      mask_logstd_grad_f64_kernel<<<1, 32, 0, st>>>(ols, act_dim, params_f64, a.log_min_std, vec_out);
-      B200RL_LAUNCH_CHECK("mask_logstd_grad_f64_kernel");
-    } else {
-      fvp_diag_f64_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, ols, act_dim, params_f64, a.log_min_std, x, reg_coeff,
-                                                           diag_scale, vec_out);
-      B200RL_LAUNCH_CHECK("fvp_diag_f64_kernel");
-    }
-  }
+  FinArgs f{};
+  f.nblocks = grid; f.scale = scale; f.count = count; f.ols = ols; f.A = act_dim;
+  f.params64 = params_f64; f.log_min_std = a.log_min_std;
+  if (mode != MODE_LOSS) { f.partial = ws; f.K = P; f.vec_out = vec_out; }
+  f.post = (mode == MODE_GRAD) ? FIN_GRAD : (mode == MODE_FVP ? FIN_FVP : FIN_NONE);
+  if (mode == MODE_FVP) { f.x = x; f.reg = reg_coeff; f.diag_scale = diag_scale; }
   if (mode != MODE_FVP && loss_out != nullptr) {
-    const double* sc = (mode == MODE_LOSS) ? ws : ws + (size_t)grid * P;
-    double* tmp = ws + (size_t)grid * (P + 3) + 8;
-    int rc = launch_finalize_sum(sc, grid, 3, loss_out, scale, st);
-    if (rc) return rc;
-    rc = launch_finalize_max(sc, grid, 3, tmp, st);
-    if (rc) return rc;
-    B200RL_CUDA_CHECK(cudaMemcpyAsync(loss_out + 2, tmp + 2, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    f.tri_partial = (mode == MODE_LOSS) ? ws : ws + (size_t)grid * P;
+    f.NT = 3; f.tri_out = loss_out;
   }
-  return 0;
+  return launch_finalize_update(f, st);
 }
 }

@@ -304,13 +304,14 @@ __global__ void __launch_bounds__(NTH, (N::H1 == 32 ? 2 : 1)) update_gemm_kernel
     __syncthreads();
   };
 
-  const long long ntiles = (a.B + G_TS - 1) / G_TS;
+  const long long ntiles = n_tiles_of(a, G_TS);
   int since_flush = 0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (long long ti_ = blockIdx.x; ti_ < ntiles; ti_ += gridDim.x) {
     asm volatile("" ::: "memory");
+    const long long tile = tile_at(a, ti_);
     const bool own_sample = (NTH == G_TS) || tid < G_TS;      // "thread = sample" phases (S0, S3)
     const long long s = tile * G_TS + tid;
-    const bool valid = own_sample && s < a.B;
+    const bool valid = own_sample && sample_valid(a, s);
     const long long sl = (s < a.B) ? s : a.B - 1;
     // ---- S0: observations
     if (own_sample) {
@@ -548,42 +549,27 @@ template <class N, int MODE, int NTH>
 static int launch_gemm_nth(const UpdArgs& a, int* grid_out, cudaStream_t st) {
   using SM = GemmSmem<N, MODE>;
   constexpr int G_THREADS = NTH;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B200RL_CUDA_CHECK(cudaFuncSetAttribute(update_gemm_kernel<N, MODE, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)SM::bytes));
-    attr_done = true;
-  }
+  B200RL_SET_MAX_SMEM((update_gemm_kernel<N, MODE, NTH>), SM::bytes);
   int per_sm = (int)((227 * 1024) / (SM::bytes + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > (N::H1 == 32 ? 2 : 1)) per_sm = (N::H1 == 32 ? 2 : 1);
   long long grid = (long long)num_sms() * per_sm;
-  const long long ntiles = (a.B + G_TS - 1) / G_TS;
+  const long long ntiles = host_n_tiles(a, G_TS);
   if (grid > ntiles) grid = ntiles;
   if (grid > MAX_PARTIAL_BLOCKS) grid = MAX_PARTIAL_BLOCKS;
+  if (grid < 1) grid = 1;
   update_gemm_kernel<N, MODE, NTH><<<(unsigned)grid, G_THREADS, SM::bytes, st>>>(a);
   B200RL_LAUNCH_CHECK("update_gemm_kernel");
   *grid_out = (int)grid;
   return 0;
 }
 
-// threads per tile: 128 for 32-wide nets; 64-wide nets: env B200RL_GEMM_THREADS = 128 | 256 (default 256: no
-// spills, two warps per scheduler -- Hopper FVP 4.7 -> 3.0 ms, grad 3.2 -> 2.4 ms)
-static int gemm_threads_64() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("B200RL_GEMM_THREADS");
-    cached = (e != nullptr && atoi(e) == 128) ? 128 : 256;
-  }
-  return cached;
-}
-
+// threads per tile: 128 for 32-wide nets, 256 for 64-wide nets (8 samples x 4 units per thread: no spills, two warps per
+// scheduler -- Hopper FVP 4.7 -> 3.0 ms, gradient 3.2 -> 2.4 ms against the 128-thread variant, A/B measured in round 1)
 template <class N, int MODE>
 static int launch_gemm(const UpdArgs& a, int* grid_out, cudaStream_t st) {
-  if constexpr (N::H1 == 64) {
-    if (gemm_threads_64() == 256) return launch_gemm_nth<N, MODE, 256>(a, grid_out, st);
-  }
-  return launch_gemm_nth<N, MODE, 128>(a, grid_out, st);
+  if constexpr (N::H1 == 64) return launch_gemm_nth<N, MODE, 256>(a, grid_out, st);
+  else return launch_gemm_nth<N, MODE, 128>(a, grid_out, st);
 }
 
 int update_gemm_launch(int mode, int obs_dim, int h, int act_dim, const UpdArgs& a, int* grid_out, int* P_out,

@@ -14,10 +14,6 @@
 namespace b200rl {
 
 constexpr int T_THREADS = 128, T_TILE = 128, T_LD = T_TILE + 4;
-#ifdef B200RL_CONST_WEIGHTS
-B200RL_DEFINE_CONST_THETA
-#endif
-
 
 template <class N, int MODE>
 struct TileSmem {
@@ -44,19 +40,13 @@ __global__ void __launch_bounds__(T_THREADS, tile_minblocks<N, MODE>()) update_t
   constexpr int O = N::O, H = 32, A = N::A, P = N::P, LD = T_LD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sf = reinterpret_cast<float*>(smem_raw);
-#ifdef B200RL_CONST_WEIGHTS
-  const float* sp = c_theta;               // the FVP tangent (sv) stays in shared memory in this variant
-#else
   float* sp = sf + SM::o_sp;
-#endif
   float* sv = sf + SM::o_sv;
   float* stage = sf + SM::o_stage;
   double* red_scratch = reinterpret_cast<double*>(smem_raw + SM::scratch_off);
   const int tid = threadIdx.x;
 
-#ifndef B200RL_CONST_WEIGHTS
   for (int i = tid; i < P; i += T_THREADS) sp[i] = a.params[i];
-#endif
   if constexpr (MODE == MODE_FVP)
     for (int i = tid; i < P; i += T_THREADS) sv[i] = (float)a.xvec[i];
   __syncthreads();
@@ -95,13 +85,14 @@ __global__ void __launch_bounds__(T_THREADS, tile_minblocks<N, MODE>()) update_t
   for (int k = 0; k < NS; ++k) accS[k] = 0.0;
   double s_loss = 0.0, s_kl = 0.0, m_kl = -1.0e300;
 
-  const long long ntiles = (a.B + T_TILE - 1) / T_TILE;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const long long ntiles = n_tiles_of(a, T_TILE);
+  for (long long ti_ = blockIdx.x; ti_ < ntiles; ti_ += gridDim.x) {
     asm volatile("" ::: "memory");
-    const long long s = tile * T_TILE + tid;
-    const bool valid = s < a.B;
+    const long long s = tile_at(a, ti_) * T_TILE + tid;
+    const bool inrange = s < a.B;
+    const bool valid = sample_valid(a, s);
     // ================= phase A: per-sample forward / (tangent) / backward, staged to shared memory
-    tile_phase_a<N, MODE, SM, LD>(a, sp, sv, stage, D, valid ? s : a.B - 1, valid, tid, s_loss, s_kl, m_kl);
+    tile_phase_a<N, MODE, SM, LD>(a, sp, sv, stage, D, inrange ? s : a.B - 1, inrange, valid, tid, s_loss, s_kl, m_kl);
     __syncthreads();
     // ================= phase B: Gram accumulation over the tile
     {
@@ -227,25 +218,15 @@ __global__ void __launch_bounds__(T_THREADS, tile_minblocks<N, MODE>()) update_t
 template <class N, int MODE>
 static int launch_tile(const UpdArgs& a, int* grid_out, cudaStream_t st) {
   using SM = TileSmem<N, MODE>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B200RL_CUDA_CHECK(cudaFuncSetAttribute(update_tile_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)SM::bytes));
-    attr_done = true;
-  }
+  B200RL_SET_MAX_SMEM((update_tile_kernel<N, MODE>), SM::bytes);
   int per_sm = (int)((228 * 1024) / (SM::bytes + 1024));   // 228 KB per SM, 1 KB reserved per resident CTA
   if (per_sm < 1) per_sm = 1;
   if (per_sm > tile_minblocks<N, MODE>()) per_sm = tile_minblocks<N, MODE>();
   long long grid = (long long)num_sms() * per_sm;
-  const long long ntiles = (a.B + T_TILE - 1) / T_TILE;
+  const long long ntiles = host_n_tiles(a, T_TILE);
   if (grid > ntiles) grid = ntiles;
   if (grid > MAX_PARTIAL_BLOCKS) grid = MAX_PARTIAL_BLOCKS;
-#ifdef B200RL_CONST_WEIGHTS
-  {
-    int rc_up = upload_theta(a.params, N::P, st);
-    if (rc_up) return rc_up;
-  }
-#endif
+  if (grid < 1) grid = 1;
   update_tile_kernel<N, MODE><<<(unsigned)grid, T_THREADS, SM::bytes, st>>>(a);
   B200RL_LAUNCH_CHECK("update_tile_kernel");
   *grid_out = (int)grid;

@@ -24,12 +24,12 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
 
 __global__ void __launch_bounds__(VEC_THREADS)
     cg_init_kernel(long long P, const double* __restrict__ g, double* __restrict__ x, double* __restrict__ r,
-                   double* __restrict__ p, double* __restrict__ st) {
+                   double* __restrict__ p, double* __restrict__ st, int p_f32) {
   __shared__ double scratch[32];
   double acc = 0.0;
   for (long long i = threadIdx.x; i < P; i += blockDim.x) {
     const double gi = g[i];
-    x[i] = 0.0; r[i] = gi; p[i] = gi;
+    x[i] = 0.0; r[i] = gi; p[i] = p_f32 ? (double)(float)gi : gi;
     acc += gi * gi;
   }
   const double rdotr = block_sum(acc, scratch);
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(VEC_THREADS)
 // one krylov.cg iteration given z = A p  (krylov.py:25-35); a no-op once rdotr < tol was seen (the reference breaks)
 __global__ void __launch_bounds__(VEC_THREADS)
     cg_step_kernel(long long P, const double* __restrict__ z, double* __restrict__ x, double* __restrict__ r,
-                   double* __restrict__ p, double* __restrict__ st, double tol) {
+                   double* __restrict__ p, double* __restrict__ st, double tol, int p_f32) {
   __shared__ double scratch[32];
   if (st[1] != 0.0) return;  // uniform across the block
   const double rdotr = st[0];
@@ -56,7 +56,13 @@ __global__ void __launch_bounds__(VEC_THREADS)
   }
   const double newrdotr = block_sum(acc, scratch);
   const double mu = newrdotr / rdotr;
-  for (long long i = threadIdx.x; i < P; i += blockDim.x) p[i] = r[i] + mu * p[i];
+  // p_f32: the search direction is kept exactly representable in float32 -- the precision in which the Fisher-vector
+  // kernel reads it -- so that z = A p is the product with the very vector the recurrences use (an A p~ paired with an
+  // unrounded p is an inconsistent matvec, which CG on this ill-conditioned system amplifies)
+  for (long long i = threadIdx.x; i < P; i += blockDim.x) {
+    const double pn = r[i] + mu * p[i];
+    p[i] = p_f32 ? (double)(float)pn : pn;
+  }
   if (threadIdx.x == 0) {
     st[0] = newrdotr;
     st[2] = pz;
@@ -161,8 +167,25 @@ __global__ void __launch_bounds__(64) lfb_solve_kernel(const double* __restrict_
     reg *= 10.0;
     __syncthreads();
   }
-  for (int i = tid; i < d; i += blockDim.x) w_out[i] = wv[i];
+  // all 5 attempts failed: the triangular solve never ran (wv is not defined) -- write zeros (= "no baseline"), never
+  // uninitialised memory; info[2] = 0 reports it
+  for (int i = tid; i < d; i += blockDim.x) w_out[i] = ok ? wv[i] : 0.0;
   if (tid == 0) { info[0] = reg; info[1] = (double)attempt; info[2] = (double)ok; }
+}
+
+// out[i] = sum over ranks (i < n_sum) or max over ranks (i >= n_sum) of gathered[r][i], in rank order: the local half of
+// the all-gather based "mixed all-reduce" (rllab_b200/parallel.py) -- one collective for a vector that carries sums and
+// maxima, and a reduction order that is fixed by construction (bit-identical on every rank).
+__global__ void reduce_ranks_kernel(const double* __restrict__ gathered, int world, long long n, long long n_sum,
+                                    double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = gathered[i];
+  for (int r = 1; r < world; ++r) {
+    const double v = gathered[(size_t)r * n + i];
+    acc = (i < n_sum) ? acc + v : fmax(acc, v);
+  }
+  out[i] = acc;
 }
 
 __global__ void f64_to_f32_kernel(long long n, const double* __restrict__ s, float* __restrict__ d) {
@@ -176,17 +199,18 @@ using namespace b200rl;
 
 extern "C" {
 
-int b200rl_cg_init(long long P, const double* g, double* x, double* r, double* p, double* cg_state, void* stream) {
+int b200rl_cg_init(long long P, const double* g, double* x, double* r, double* p, double* cg_state, int p_f32,
+                   void* stream) {
   B200RL_REQUIRE(P > 0 && g && x && r && p && cg_state, "cg_init: bad arguments");
-  cg_init_kernel<<<1, VEC_THREADS, 0, (cudaStream_t)stream>>>(P, g, x, r, p, cg_state);
+  cg_init_kernel<<<1, VEC_THREADS, 0, (cudaStream_t)stream>>>(P, g, x, r, p, cg_state, p_f32);
   B200RL_LAUNCH_CHECK("cg_init_kernel");
   return 0;
 }
 
 int b200rl_cg_step(long long P, const double* z, double* x, double* r, double* p, double* cg_state,
-                   double residual_tol, void* stream) {
+                   double residual_tol, int p_f32, void* stream) {
   B200RL_REQUIRE(P > 0 && z && x && r && p && cg_state, "cg_step: bad arguments");
-  cg_step_kernel<<<1, VEC_THREADS, 0, (cudaStream_t)stream>>>(P, z, x, r, p, cg_state, residual_tol);
+  cg_step_kernel<<<1, VEC_THREADS, 0, (cudaStream_t)stream>>>(P, z, x, r, p, cg_state, residual_tol, p_f32);
   B200RL_LAUNCH_CHECK("cg_step_kernel");
   return 0;
 }
@@ -223,6 +247,13 @@ int b200rl_lfb_solve(int obs_dim, const double* gram, double reg_coeff, double* 
   B200RL_REQUIRE(gram && w_out && info_out && obs_dim > 0 && 2 * obs_dim + 4 <= LFB_DMAX, "lfb_solve: bad arguments");
   lfb_solve_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(gram, 2 * obs_dim + 4, reg_coeff, w_out, info_out);
   B200RL_LAUNCH_CHECK("lfb_solve_kernel");
+  return 0;
+}
+
+int b200rl_reduce_ranks(const double* gathered, int world, long long n, long long n_sum, double* out, void* stream) {
+  B200RL_REQUIRE(gathered && out && world >= 1 && n > 0 && n_sum >= 0 && n_sum <= n, "reduce_ranks: bad arguments");
+  reduce_ranks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gathered, world, n, n_sum, out);
+  B200RL_LAUNCH_CHECK("reduce_ranks_kernel");
   return 0;
 }
 

@@ -58,11 +58,20 @@ class LaneBatch(object):
         self.adv = torch.empty((T, N), dtype=F32, device=device)
         self.ret = torch.empty((T, N), dtype=F32, device=device)
         self.base = torch.empty((T, N), dtype=F32, device=device)
-        self.sums = torch.zeros((L.PS_NSUM,), dtype=F64, device=device)
-        self.maxs = torch.zeros((L.PS_NMAX,), dtype=F64, device=device)
+        # reduction block of process_samples + the baseline fit, contiguous so that ONE collective carries all of it:
+        # [sums (PS_NSUM) | LinearFeatureBaseline normal equations (d+1)(d+2)/2 | maxs (PS_NMAX)]
+        d1 = 2 * O + 5
+        self.n_gram = d1 * (d1 + 1) // 2
+        self.red = torch.zeros((L.PS_NSUM + self.n_gram + L.PS_NMAX,), dtype=F64, device=device)
+        self.sums = self.red[:L.PS_NSUM]
+        self.gram = self.red[L.PS_NSUM:L.PS_NSUM + self.n_gram]
+        self.maxs = self.red[L.PS_NSUM + self.n_gram:]
+        self.n_red_sum = L.PS_NSUM + self.n_gram      # leading entries that are sums (the rest are maxima)
+        self.count = self.sums[2:3]   # device-resident number of valid samples over all ranks (after the all-reduce)
         self.version = 0              # bumped by the sampler whenever the contents change
         self.processed = False        # adv/ret/base valid (process_samples has run on this rollout)
         self.B_global = N * T         # samples over all ranks (the sampler overwrites it under torchrun)
+        self.masked = False           # process_samples dropped cut paths: passes read FLAG_MASKED and the device count
 
     @property
     def B(self):
@@ -75,6 +84,12 @@ class LaneBatch(object):
             hc = torch.empty((h1 + h2, self.T, self.N), dtype=F32, device=self.device)
             self._hcache = hc
         return hc
+
+    def valid_mask(self):
+        """(T, N) bool host array: samples that are not part of a dropped (cut) path."""
+        if not self.masked:
+            return np.ones((self.T, self.N), dtype=bool)
+        return (self.flags.cpu().numpy() & L.FLAG_MASKED) == 0
 
     def to_numpy(self):
         """Host copy in the oracle's dict layout (tests / path materialisation)."""
@@ -116,26 +131,35 @@ def rollout(kind, params32, h1, h2, min_std, batch, max_path_length, eps=None, r
            L.ptr(b.flags), L.ptr(b.tstep), L.ptr(b.log_std), _stream())
 
 
-def process_samples(batch, w, discount, gae_lambda):
+def process_samples(batch, w, discount, gae_lambda, drop_cut_paths=False):
     b = batch
     _chk(w, F64, "w", 2 * b.O + 4)
     L.call("b200rl_process_samples", b.O, b.N, b.T, L.ptr(b.obs), L.ptr(b.rew), L.ptr(b.flags), L.ptr(b.tstep),
-           L.ptr(w), float(discount), float(gae_lambda), L.ptr(b.adv), L.ptr(b.ret), L.ptr(b.base), L.ptr(b.sums),
-           L.ptr(b.maxs), L.ptr(workspace(b.device)), _stream())
+           L.ptr(w), float(discount), float(gae_lambda), int(bool(drop_cut_paths)), L.ptr(b.adv), L.ptr(b.ret),
+           L.ptr(b.base), L.ptr(b.sums), L.ptr(b.maxs), L.ptr(workspace(b.device)), _stream())
+    b.masked = bool(drop_cut_paths)
+
+
+def _mask(batch):
+    """(flags pointer, scale, count pointer) of an update pass over `batch`: with dropped paths the kernels skip
+    FLAG_MASKED samples and divide by the device-resident valid-sample count; otherwise by B_global on the host."""
+    if batch.masked:
+        return L.ptr(batch.flags), 1.0, L.ptr(batch.count)
+    return None, 1.0 / batch.B_global, None
 
 
 def center_advantages(batch, center, positive):
     b = batch
-    L.call("b200rl_center_advantages", L.ptr(b.adv), b.B, L.ptr(b.sums), L.ptr(b.maxs), int(center), int(positive),
-           _stream())
+    L.call("b200rl_center_advantages", L.ptr(b.adv), b.B, L.ptr(b.flags) if b.masked else None, L.ptr(b.sums),
+           L.ptr(b.maxs), int(center), int(positive), _stream())
 
 
 def lfb_gram(batch, gram_out):
     b = batch
     d1 = 2 * b.O + 5
     _chk(gram_out, F64, "gram_out", d1 * (d1 + 1) // 2)
-    L.call("b200rl_lfb_gram", b.O, b.B, L.ptr(b.obs), L.ptr(b.tstep), L.ptr(b.ret), L.ptr(gram_out),
-           L.ptr(workspace(b.device)), _stream())
+    L.call("b200rl_lfb_gram", b.O, b.B, L.ptr(b.obs), L.ptr(b.tstep), L.ptr(b.ret),
+           L.ptr(b.flags) if b.masked else None, L.ptr(gram_out), L.ptr(workspace(b.device)), _stream())
 
 
 def lfb_solve(obs_dim, gram, reg_coeff, w_out, info_out):
@@ -143,49 +167,65 @@ def lfb_solve(obs_dim, gram, reg_coeff, w_out, info_out):
     L.call("b200rl_lfb_solve", obs_dim, L.ptr(gram), float(reg_coeff), L.ptr(w_out), L.ptr(info_out), _stream())
 
 
-def loss_kl(loss_kind, params32, dims, min_std, batch, scale, out):
+def loss_kl(loss_kind, params32, dims, min_std, batch, out):
+    """out[3] = (surrogate loss, mean KL, max KL) of this rank's samples, already divided by the global sample count."""
     O, h1, h2, A = dims
     b = batch
+    fl, scale, cnt = _mask(b)
     _chk(params32, F32, "params32"), _chk(out, F64, "out", 3)
     L.call("b200rl_loss_kl", loss_kind, L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
-           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), float(scale), L.ptr(out),
+           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), fl, scale, cnt, L.ptr(out),
            L.ptr(workspace(b.device)), _stream())
 
 
-def grad(loss_kind, params32, dims, min_std, batch, scale, g_out, loss_out=None, h_cache=None):
+def grad(loss_kind, params32, dims, min_std, batch, g_out, loss_out=None, h_cache=None):
     O, h1, h2, A = dims
     b = batch
+    fl, scale, cnt = _mask(b)
     _chk(params32, F32, "params32"), _chk(g_out, F64, "g_out")
     L.call("b200rl_grad", loss_kind, L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
-           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), float(scale), L.ptr(g_out), L.ptr(loss_out),
+           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), fl, scale, cnt, L.ptr(g_out), L.ptr(loss_out),
            L.ptr(h_cache), L.ptr(workspace(b.device)), _stream())
 
 
-def fvp(params32, dims, min_std, batch, x, scale, reg_coeff, diag_scale, Hx_out, h_cache=None):
+def fvp(params32, dims, min_std, batch, x, reg_coeff, diag_scale, Hx_out, h_cache=None, tile_list=None, count=None):
+    """tile_list (int32 device tensor) + count (float64 device scalar: valid samples in those tiles over all ranks):
+    the sub-sampled product of subsample_factor < 1."""
     O, h1, h2, A = dims
     b = batch
+    fl, scale, cnt = _mask(b)
+    if tile_list is not None:
+        scale, cnt = 1.0, L.ptr(count)
     _chk(params32, F32, "params32"), _chk(x, F64, "x"), _chk(Hx_out, F64, "Hx_out", x.numel())
-    L.call("b200rl_fvp", L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs), L.ptr(x),
-           float(scale), float(reg_coeff), float(diag_scale), L.ptr(Hx_out), L.ptr(h_cache), L.ptr(workspace(b.device)),
-           _stream())
+    L.call("b200rl_fvp", L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs), fl, L.ptr(x), scale,
+           cnt, float(reg_coeff), float(diag_scale), L.ptr(Hx_out), L.ptr(h_cache), L.ptr(tile_list),
+           0 if tile_list is None else int(tile_list.numel()), L.ptr(workspace(b.device)), _stream())
 
 
-def update_f64(mode, loss_kind, params64, dims, min_std, batch, x, scale, reg_coeff, diag_scale, vec_out, loss_out):
+def count_valid(batch, tile_list, out):
+    b = batch
+    L.call("b200rl_count_valid", b.B, L.ptr(b.flags) if b.masked else None, L.ptr(tile_list),
+           0 if tile_list is None else int(tile_list.numel()), L.ptr(out), L.ptr(workspace(b.device)), _stream())
+
+
+def update_f64(mode, loss_kind, params64, dims, min_std, batch, x, reg_coeff, diag_scale, vec_out, loss_out):
     """float64 parity-mode pass: mode 0 loss/KL, 1 gradient (+loss), 2 Fisher-vector product."""
     O, h1, h2, A = dims
     b = batch
+    fl, scale, cnt = _mask(b)
     _chk(params64, F64, "params64"), _chk(x, F64, "x"), _chk(vec_out, F64, "vec_out"), _chk(loss_out, F64, "loss_out", 3)
     L.call("b200rl_update_f64", mode, loss_kind, L.ptr(params64), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
-           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), L.ptr(x), float(scale), float(reg_coeff),
+           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), fl, L.ptr(x), scale, cnt, float(reg_coeff),
            float(diag_scale), L.ptr(vec_out), L.ptr(loss_out), L.ptr(workspace(b.device)), _stream())
 
 
-def cg_init(g, x, r, p, st):
-    L.call("b200rl_cg_init", g.numel(), L.ptr(g), L.ptr(x), L.ptr(r), L.ptr(p), L.ptr(st), _stream())
+def cg_init(g, x, r, p, st, p_f32=False):
+    L.call("b200rl_cg_init", g.numel(), L.ptr(g), L.ptr(x), L.ptr(r), L.ptr(p), L.ptr(st), int(bool(p_f32)), _stream())
 
 
-def cg_step(z, x, r, p, st, tol=1e-10):
-    L.call("b200rl_cg_step", z.numel(), L.ptr(z), L.ptr(x), L.ptr(r), L.ptr(p), L.ptr(st), float(tol), _stream())
+def cg_step(z, x, r, p, st, tol=1e-10, p_f32=False):
+    L.call("b200rl_cg_step", z.numel(), L.ptr(z), L.ptr(x), L.ptr(r), L.ptr(p), L.ptr(st), float(tol), int(bool(p_f32)),
+           _stream())
 
 
 def trpo_step_size(x, Hx, delta, step_out, info_out):
@@ -205,6 +245,11 @@ def adam_step(theta64, theta32, g, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8)
 
 def f64_to_f32(src, dst):
     L.call("b200rl_f64_to_f32", src.numel(), L.ptr(src), L.ptr(dst), _stream())
+
+
+def reduce_ranks(gathered, world, n, n_sum, out):
+    _chk(gathered, F64, "gathered", world * n), _chk(out, F64, "out", n)
+    L.call("b200rl_reduce_ranks", L.ptr(gathered), int(world), int(n), int(n_sum), L.ptr(out), _stream())
 
 
 def planes_to_rows_f64(src, dim, B, dst):

@@ -21,7 +21,7 @@ class FirstOrderOptimizer(object):
         self._target = None
         self._loss_kind = L.LOSS_VPG
         self._comm = None
-        self._m = self._v = self._g = self._out = None
+        self._m = self._v = self._g = self._gl = self._gout = self._out = None
         self._t = 0
         self._cache = None
         self._g_key = None
@@ -38,7 +38,8 @@ class FirstOrderOptimizer(object):
         P = self._target.n_params
         if self._m is None or self._m.device != dev:
             z = lambda n=P: torch.zeros(n, dtype=torch.float64, device=dev)
-            self._m, self._v, self._g, self._out = z(), z(), z(), z(3)
+            self._gl = z(P + 3)          # [flat gradient | loss, sum KL | max KL]: one collective carries all of it
+            self._m, self._v, self._g, self._gout, self._out = z(), z(), self._gl[:P], self._gl[P:], z(3)
 
     def _eval(self, batch, want_grad=False):
         """(loss, mean_kl, max_kl); want_grad runs the gradient pass, which yields the triple for free and leaves the
@@ -49,18 +50,19 @@ class FirstOrderOptimizer(object):
         if self._cache is not None and self._cache[0] == key:
             return self._cache[1]
         self._state(batch.device)
+        active = self._comm is not None and self._comm.active
         if want_grad:
-            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, self._g,
-                     self._out)
-            if self._comm is not None and self._comm.active:
-                self._comm.all_reduce_sum(self._g)
+            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, self._g, self._gout)
+            if active:
+                self._comm.all_reduce_mixed(self._gl, pol.n_params + 2)
             self._g_key = key
+            src = self._gout
         else:
-            ops.loss_kl(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, self._out)
-        if self._comm is not None and self._comm.active:
-            self._comm.all_reduce_sum(self._out[:2])
-            self._comm.all_reduce_max(self._out[2:])
-        vals = ops.LazyTriple(self._out)      # pinned-memory readback queued behind the pass; blocks when indexed
+            ops.loss_kl(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, self._out)
+            if active:
+                self._comm.all_reduce_mixed(self._out, 2)
+            src = self._out
+        vals = ops.LazyTriple(src)            # pinned-memory readback queued behind the pass; blocks when indexed
         self._cache = (key, vals)
         return vals
 
@@ -87,9 +89,9 @@ class FirstOrderOptimizer(object):
         last = self._eval(batch, want_grad=True)
         for epoch in range(self._max_epochs):
             if self._g_key != (pol.version, id(batch), batch.version):
-                ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, 1.0 / batch.B_global, self._g)
+                ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, self._g, self._gout)
                 if self._comm is not None and self._comm.active:
-                    self._comm.all_reduce_sum(self._g)
+                    self._comm.all_reduce_mixed(self._gl, pol.n_params + 2)
             self._t += 1
             ops.adam_step(pol.theta64, pol.theta32, self._g, self._m, self._v, self._t, self._learning_rate, self._b1,
                           self._b2, self._eps)
@@ -108,15 +110,22 @@ class FirstOrderOptimizer(object):
 
     def __getstate__(self):
         d = dict(self.__dict__)
-        for k in ("_m", "_v", "_g", "_out"):
+        for k in ("_m", "_v"):
             d[k] = None if d[k] is None else d[k].cpu().numpy()
+        for k in ("_g", "_gl", "_gout", "_out"):
+            d[k] = None
         d["_cache"] = None
+        d["_g_key"] = None
         d["_comm"] = None
         return d
 
     def __setstate__(self, d):
         import torch
         self.__dict__.update(d)
-        for k in ("_m", "_v", "_g", "_out"):
-            if self.__dict__[k] is not None:
-                self.__dict__[k] = torch.as_tensor(self.__dict__[k]).cuda()
+        if self._m is not None:
+            P = len(self._m)
+            self._m, self._v = (torch.as_tensor(self.__dict__[k]).cuda() for k in ("_m", "_v"))
+            dev = self._m.device
+            self._gl = torch.zeros(P + 3, dtype=torch.float64, device=dev)
+            self._g, self._gout = self._gl[:P], self._gl[P:]
+            self._out = torch.zeros(3, dtype=torch.float64, device=dev)

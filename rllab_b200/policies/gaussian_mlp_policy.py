@@ -100,9 +100,17 @@ class GaussianMLPPolicy(object):
         import torch
         if getattr(self, "_pin", None) is None:
             self._pin = torch.empty(self.n_params, dtype=torch.float64).pin_memory()   # page-locked staging buffer
+        # the single pinned staging buffer may still be the source of an earlier, queued host->device copy: wait for that
+        # copy (an event recorded right behind it) before overwriting the buffer
+        ev = getattr(self, "_pin_event", None)
+        if ev is not None:
+            ev.synchronize()
         self._pin.copy_(torch.as_tensor(flat))
         self._theta64.copy_(self._pin, non_blocking=True)
-        self._theta32.copy_(self._theta64)            # value.astype(dtype), parameterized.py:68
+        self._pin_event = torch.cuda.Event()
+        self._pin_event.record()
+        from .. import ops
+        ops.f64_to_f32(self._theta64, self._theta32)  # value.astype(dtype), parameterized.py:68
 
     def get_param_shapes(self, **tags):
         return self._shapes()

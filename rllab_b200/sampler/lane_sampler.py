@@ -9,10 +9,17 @@ process_samples(...)  baseline predict + GAE + returns + statistics (b200rl_proc
                       (b200rl_center_advantages), then -- after the advantages, as base.py:163-167 -- the baseline
                       fit (b200rl_lfb_gram + b200rl_lfb_solve); records the same tabular keys (base.py:170-180).
 
-Batch geometry: T = max_path_length steps per lane, N = ceil(batch_size / T) lanes in total (>= batch_size samples,
-whole paths, like the reference's threshold semantics stateful_pool.py:149-152), sharded contiguously over ranks.
-Every lane runs exactly T steps with auto-reset on `done`; a path cut by the end of the buffer is kept as a
-truncated path (the reference does the same to the last path in truncate_paths, parallel_sampler.py:129-155).
+Batch geometry: T = max_path_length steps per lane, N = ceil(batch_size / T) lanes in total, sharded contiguously over
+ranks.  Every lane runs exactly T steps with auto-reset on `done`.  The path a lane is in when its buffer ends is cut
+short by the sampler, not by the env; what happens to it follows the reference's `whole_paths` switch
+(batch_polopt.py:30-34):
+  whole_paths=True  (default)  only whole paths are returned, as BatchSampler does (and as the vectorized sampler does
+                    when it drops its unfinished running_paths, sandbox/rocky/tf/samplers/vectorized_sampler.py): the cut
+                    path is dropped -- FLAG_MASKED on its samples, no contribution to advantages, baseline fit, losses,
+                    NumTrajs or the return statistics.  The first path of every lane always completes (T =
+                    max_path_length), so no lane is empty.
+  whole_paths=False the cut path is kept as a truncated path, which is what truncate_paths does to the last path of
+                    the batch (parallel_sampler.py:129-155); every (t, lane) cell is then a valid sample.
 """
 import numpy as np
 
@@ -24,13 +31,14 @@ from .base import Sampler
 class LanePaths(object):
     """Handle on the device trajectories of one iteration (duck-types the reference's `paths` list lazily)."""
 
-    def __init__(self, batch):
+    def __init__(self, batch, whole_paths=True):
         self.lane_batch = batch
+        self.whole_paths = whole_paths
         self._paths = None
 
     def to_paths(self):
         if self._paths is None:
-            self._paths = lanes_to_paths(self.lane_batch)
+            self._paths = lanes_to_paths(self.lane_batch, self.whole_paths)
         return self._paths
 
     def __len__(self):
@@ -43,9 +51,10 @@ class LanePaths(object):
         return self.to_paths()[i]
 
 
-def lanes_to_paths(batch):
+def lanes_to_paths(batch, whole_paths=True):
     """Device lanes -> list of path dicts {observations (L,O), actions (L,A), rewards (L,), agent_infos{mean,log_std},
-    env_infos{}} (+ advantages / returns when process_samples has run), lane-major then time order."""
+    env_infos{}} (+ advantages / returns when process_samples has run), lane-major then time order.  whole_paths: leave
+    out the paths cut by the end of the lane buffer (FLAG_CUT on their last sample)."""
     t = batch.to_numpy()
     O, T, N = t["obs"].shape
     A = t["act"].shape[0]
@@ -58,6 +67,9 @@ def lanes_to_paths(batch):
         start = 0
         for e in np.nonzero(ends[:, n])[0]:
             sl = slice(start, e + 1)
+            if whole_paths and (t["flags"][e, n] & L.FLAG_CUT):
+                start = e + 1
+                continue
             p = dict(
                 observations=t["obs"][:, sl, n].T.astype(np.float64),
                 actions=t["act"][:, sl, n].T.astype(np.float64),
@@ -94,7 +106,8 @@ class SamplesData(dict):
         def rows(src, dim):
             dst = torch.empty((b.B, dim), dtype=torch.float64, device=b.device)
             ops.planes_to_rows_f64(src, dim, b.B, dst)
-            return dst.cpu().numpy()
+            out = dst.cpu().numpy()
+            return out[b.valid_mask().reshape(-1)] if b.masked else out      # dropped paths are not samples
         if key == "observations":
             v = rows(b.obs, b.O)
         elif key == "actions":
@@ -102,8 +115,9 @@ class SamplesData(dict):
         elif key in ("rewards", "returns", "advantages"):
             v = rows(dict(rewards=b.rew, returns=b.ret, advantages=b.adv)[key], 1).reshape(-1)
         elif key == "agent_infos":
-            v = dict(mean=rows(b.mean, b.A),
-                     log_std=np.tile(b.log_std.double().cpu().numpy().reshape(1, -1), (b.B, 1)))
+            v_mean = rows(b.mean, b.A)
+            v = dict(mean=v_mean,
+                     log_std=np.tile(b.log_std.double().cpu().numpy().reshape(1, -1), (len(v_mean), 1)))
         elif key == "env_infos":
             v = dict()
         else:
@@ -156,6 +170,8 @@ class LaneSampler(Sampler):
         self.batch.processed = False
         self.lane0 = lane0
         self.n_total = n_total
+        logger.log("LaneSampler: %d lanes x %d steps = %d samples per iteration (batch_size %d rounded up to whole lanes); "
+                   "whole_paths=%s" % (n_total, T, n_total * T, int(algo.batch_size), bool(getattr(algo, "whole_paths", True))))
         if self.seed is None:
             self.seed = int(np.random.randint(0, 2 ** 31 - 1))
         self._sums_host = None
@@ -170,16 +186,22 @@ class LaneSampler(Sampler):
                     int(self.seed) & 0xFFFFFFFF, int(itr) & 0xFFFFFFFF, self.lane0)
         b.version += 1
         b.processed = False
-        return LanePaths(b)
+        b.masked = False
+        return LanePaths(b, bool(getattr(algo, "whole_paths", True)))
 
     def process_samples(self, itr, paths):
         from .. import ops
         algo = self.algo
         b = paths.lane_batch
         w = algo.baseline.device_weights(b.O, b.device)
-        ops.process_samples(b, w, algo.discount, algo.gae_lambda)
-        self.comm.all_reduce_sum(b.sums)
-        self.comm.all_reduce_max(b.maxs)
+        ops.process_samples(b, w, algo.discount, algo.gae_lambda, drop_cut_paths=bool(getattr(algo, "whole_paths", True)))
+        # the baseline's normal equations only need the returns: reduce them right away so that ONE collective carries
+        # the advantage sums, the normal equations and the maxima (the fit itself still follows the advantages, as in
+        # base.py:163-167 -- the order has no numerical effect)
+        lanes_fit = hasattr(algo.baseline, "gram_lanes")
+        if lanes_fit:
+            algo.baseline.gram_lanes(b)
+        self.comm.all_reduce_mixed(b.red, b.n_red_sum)
         if algo.center_adv or algo.positive_adv:
             ops.center_advantages(b, algo.center_adv, algo.positive_adv)
         b.version += 1
@@ -187,7 +209,10 @@ class LaneSampler(Sampler):
         samples_data = SamplesData(b, paths)
 
         logger.log("fitting baseline...")
-        algo.baseline.fit_lanes(b, self.comm)
+        if lanes_fit:
+            algo.baseline.solve_lanes(b)
+        else:
+            algo.baseline.fit(paths.to_paths())
         logger.log("fitted")
 
         # statistics: queued pinned-memory readbacks, resolved when the logger dumps the table (or `stats` is read), so

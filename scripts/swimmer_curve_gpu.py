@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(n_itr, env_name="swimmer"):
+def main(n_itr, env_name="swimmer", precision="f32", seed=None, policy_seed=None):
     from rllab_b200.algos.trpo import TRPO
     from rllab_b200.baselines.linear_feature_baseline import LinearFeatureBaseline
     from rllab_b200.envs.mujoco.hopper_env import HopperEnv
@@ -27,11 +27,12 @@ def main(n_itr, env_name="swimmer"):
     cfg, curve = gold["config"], gold["curve"]
     logger.set_quiet(True)
     env = normalize(HopperEnv() if env_name == "hopper" else SwimmerEnv())
-    policy = GaussianMLPPolicy(env.spec, hidden_sizes=tuple(cfg["hidden"]), seed=cfg["policy_seed"])
+    policy = GaussianMLPPolicy(env.spec, hidden_sizes=tuple(cfg["hidden"]),
+                               seed=cfg["policy_seed"] if policy_seed is None else policy_seed)
     algo = TRPO(env=env, policy=policy, baseline=LinearFeatureBaseline(env.spec), batch_size=cfg["lanes"] * cfg["horizon"],
                 max_path_length=cfg["horizon"], n_itr=n_itr, discount=cfg["discount"], gae_lambda=cfg["gae_lambda"],
-                step_size=cfg["step_size"], optimizer_args=dict(cg_iters=cfg["cg_iters"]),
-                sampler_args=dict(n_envs=cfg["lanes"], seed=cfg["seed"]))
+                step_size=cfg["step_size"], optimizer_args=dict(cg_iters=cfg["cg_iters"], precision=precision),
+                sampler_args=dict(n_envs=cfg["lanes"], seed=cfg["seed"] if seed is None else seed))
     algo.start_worker()
     algo.init_opt()
     rows = []
@@ -49,4 +50,6 @@ def main(n_itr, env_name="swimmer"):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 40, sys.argv[2] if len(sys.argv) > 2 else "swimmer")
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 40, sys.argv[2] if len(sys.argv) > 2 else "swimmer",
+         sys.argv[3] if len(sys.argv) > 3 else "f32", int(sys.argv[4]) if len(sys.argv) > 4 else None,
+         int(sys.argv[5]) if len(sys.argv) > 5 else None)

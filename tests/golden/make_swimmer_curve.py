@@ -4,7 +4,7 @@ LaneSampler(seed=SEED) on the GPU).  Purpose: north_star's "TRPO AverageReturn o
 matched sample count" -- the reference's MuJoCo Swimmer cannot run in this container, so the comparison
 target is the oracle restatement (oracle/planar.py), at N lanes x T steps per iteration.
 
-Run (CPU only, ~2 min per iteration):  python tests/golden/make_swimmer_curve.py [n_itr] [swimmer|hopper]
+Run (CPU only, ~2 min per iteration):  python tests/golden/make_swimmer_curve.py [n_itr] [swimmer|hopper] [sampler seed]
 (hopper: the cfg4 net (64,64), same keys; written to oracle_hopper_trpo_curve.json)
 """
 import json
@@ -23,9 +23,13 @@ N, T, SEED, POLICY_SEED = 1024, 500, 7, 3
 DISCOUNT, GAE_LAMBDA, STEP_SIZE, CG_ITERS = 0.99, 1.0, 0.01, 10
 
 
-def main(n_itr, env_name="swimmer"):
+def main(n_itr, env_name="swimmer", seed=None):
+    global SEED
     HIDDEN = 64 if env_name == "hopper" else 32
     OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_%s_trpo_curve.json" % env_name)
+    if seed is not None and seed != SEED:       # extra sampler seeds (same initial policy): run-to-run spread of the curve
+        SEED = seed
+        OUT = OUT.replace(".json", "_seed%d.json" % seed)
     env = E.make(env_name)
     dims = P.Dims(env.O, (HIDDEN, HIDDEN), env.A)
     theta = P.init_params(dims, np.random.RandomState(POLICY_SEED))      # == GaussianMLPPolicy(..., seed=POLICY_SEED)
@@ -57,4 +61,5 @@ def main(n_itr, env_name="swimmer"):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 40, sys.argv[2] if len(sys.argv) > 2 else "swimmer")
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 40, sys.argv[2] if len(sys.argv) > 2 else "swimmer",
+         int(sys.argv[3]) if len(sys.argv) > 3 else None)

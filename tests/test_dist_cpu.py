@@ -45,18 +45,23 @@ def test_two_rank_gloo_run_matches_single_process(tmp_path):
     rr = rng.rand(T + 1, env.K, N)
     traj = S.rollout_lanes(env, theta, dims, N, T, mpl, eps, rr)
     w = np.random.RandomState(2).randn(2 * env.O + 4) * 0.1
-    full = S.process_samples_lanes(traj, w, 0.99, 0.97, center_adv=True)
+    full = S.process_samples_lanes(traj, w, 0.99, 0.97, center_adv=True, drop_cut=True)
+    valid = full["valid"]
+    assert 0 < (~valid).sum() < valid.size                     # the case exercises dropped (cut) paths
     adv_c = np.concatenate([np.array(r["adv_c"]) for r in ranks], axis=1)
     np.testing.assert_allclose(adv_c, full["adv"], rtol=1e-10, atol=1e-12)
-    coeffs = S.lfb_fit_lanes(traj["obs"], traj["tstep"], full["ret"])
-    batch = S.batch_from_traj(traj, full["adv"])
+    coeffs = S.lfb_fit_lanes(traj["obs"], traj["tstep"], full["ret"], valid=valid)
+    batch = S.batch_from_traj(traj, full["adv"], valid)
     g = P.grad_surr(theta, batch, dims, "trpo")
+    tri = [P.surr_loss_trpo(theta, batch, dims)] + list(P.kl_stats(theta + 1e-3, batch, dims))
     x = np.random.RandomState(3).randn(dims.P)
     Hx = P.fvp(theta, batch, x, dims, 1e-5)
     for r in ranks:                      # every rank ends with the same replicated values
         np.testing.assert_allclose(r["coeffs"], coeffs, rtol=1e-6, atol=1e-8)
         np.testing.assert_allclose(r["g"], g, rtol=1e-10, atol=1e-14)
         np.testing.assert_allclose(r["Hx"], Hx, rtol=1e-10, atol=1e-14)
-        np.testing.assert_allclose(r["mx"], [full["adv_raw"].max(), -full["adv_raw"].min()], rtol=1e-12)
+        np.testing.assert_allclose(r["mx"], [full["adv_raw"][valid].max(), -full["adv_raw"][valid].min()], rtol=1e-12)
+        np.testing.assert_allclose(r["tri"], tri, rtol=1e-10, atol=1e-14)       # sums and the maximum in one message
+        assert r["n_collectives"] == 3                                         # statistics+fit, gradient+triple, FVP
     assert ranks[0]["g"] == ranks[1]["g"] and ranks[0]["coeffs"] == ranks[1]["coeffs"]     # bit-identical replicas
     assert (ranks[0]["lane0"], ranks[0]["n_local"], ranks[1]["lane0"], ranks[1]["n_local"]) == (0, 12, 12, 12)

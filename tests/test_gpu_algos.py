@@ -49,21 +49,22 @@ def _rel(a, b):
     return np.max(np.abs(a - b)) / np.max(np.abs(b))
 
 
-def _trpo_setup(env_name, hidden, cg_iters):
-    algo = _algo(env_name, "trpo", 1024, 50, hidden, optimizer_args=dict(cg_iters=cg_iters))
+def _trpo_setup(env_name, hidden, cg_iters, **opt_args):
+    algo = _algo(env_name, "trpo", 1024, 50, hidden, optimizer_args=dict(cg_iters=cg_iters, **opt_args))
     algo.start_worker()
     algo.init_opt()
     paths = algo.sampler.obtain_samples(0)
     sd = algo.sampler.process_samples(0, paths)
     b = sd.lane_batch
     theta0 = algo.policy.theta32.double().cpu().numpy()
-    batch = S.batch_from_traj(b.to_numpy(), b.adv.cpu().numpy())
+    batch = S.batch_from_traj(b.to_numpy(), b.adv.cpu().numpy(), b.valid_mask())      # whole paths only (default)
     dims = P.Dims(b.O, (hidden, hidden), b.A)
     return algo, sd, theta0, batch, dims
 
 
 @pytest.mark.parametrize("env_name,hidden,cg_iters", [("cartpole", 32, 1), ("cartpole", 32, 4), ("point", 32, 4),
-                                                      ("pendulum", 32, 4), ("cartpole", 64, 4)])
+                                                      ("pendulum", 32, 4), ("cartpole", 64, 4),
+                                                      ("swimmer", 32, 4), ("hopper", 64, 4), ("hopper", 32, 4)])
 def test_trpo_update_matches_oracle(dev, env_name, hidden, cg_iters):
     """Whole TRPO step (grad -> CG -> step size -> line search) against the float64 oracle on the same batch.
     cg_iters=1 is the reference's own test setting (tests/test_algos.py:51); 4 keeps CG inside the regime where a
@@ -124,7 +125,7 @@ def test_vpg_updates_match_oracle(dev, env_name):
             dims = P.Dims(b.O, (32, 32), b.A)
             adam = (np.zeros(dims.P), np.zeros(dims.P), 0)
         theta0 = algo.policy.get_param_values()
-        batch = S.batch_from_traj(b.to_numpy(), b.adv.cpu().numpy())
+        batch = S.batch_from_traj(b.to_numpy(), b.adv.cpu().numpy(), b.valid_mask())
         # the kernels see float32(theta); hand the oracle the same numbers
         th32 = algo.policy.theta32.double().cpu().numpy()
         g_ref = P.grad_surr(th32, batch, dims, "vpg")
@@ -174,11 +175,15 @@ def test_samples_data_wire_format(dev):
     paths = algo.sampler.obtain_samples(0)
     sd = algo.sampler.process_samples(0, paths)
     b = sd.lane_batch
-    assert sd["observations"].shape == (b.B, 2) and sd["actions"].shape == (b.B, 2)
-    assert sd["advantages"].shape == (b.B,) and sd["agent_infos"]["mean"].shape == (b.B, 2)
-    np.testing.assert_array_equal(sd["observations"], b.obs.cpu().numpy().reshape(2, -1).T.astype(np.float64))
+    valid = b.valid_mask().reshape(-1)               # whole paths only: the samples of cut paths are not samples
+    nv = int(valid.sum())
+    assert 0 < nv <= b.B == 64 * 30
+    assert sd["observations"].shape == (nv, 2) and sd["actions"].shape == (nv, 2)
+    assert sd["advantages"].shape == (nv,) and sd["agent_infos"]["mean"].shape == (nv, 2)
+    assert sd["agent_infos"]["log_std"].shape == (nv, 2)
+    np.testing.assert_array_equal(sd["observations"], b.obs.cpu().numpy().reshape(2, -1).T.astype(np.float64)[valid])
     plist = sd["paths"]
-    assert sum(len(p["rewards"]) for p in plist) == b.B == 64 * 30
+    assert sum(len(p["rewards"]) for p in plist) == nv
     assert abs(sd["advantages"].mean()) < 1e-5 and abs(sd["advantages"].std() - 1) < 1e-3      # centered
     p0 = plist[0]
     assert set(p0) >= {"observations", "actions", "rewards", "agent_infos", "env_infos", "advantages", "returns"}
@@ -286,7 +291,7 @@ def test_trpo_f64_mode_matches_oracle(dev, env_name, hidden, cg_iters, tol):
     sd = algo.sampler.process_samples(0, paths)
     b = sd.lane_batch
     theta0 = algo.policy.get_param_values()                     # float64 master parameters
-    batch = S.batch_from_traj(b.to_numpy(), b.adv.cpu().numpy())
+    batch = S.batch_from_traj(b.to_numpy(), b.adv.cpu().numpy(), b.valid_mask())
     dims = P.Dims(b.O, (hidden, hidden), b.A)
     algo.optimize_policy(0, sd)
     theta_dev = algo.policy.get_param_values()

@@ -73,12 +73,12 @@ def test_returns_and_advantages_satisfy_their_recurrences(full):
 def test_loss_and_kl_are_exact_at_theta_old(full):
     L, ops, b, th32 = full["L"], full["ops"], full["b"], full["th32"]
     out = torch.zeros(3, dtype=torch.float64, device=full["dev"])
-    ops.loss_kl(L.LOSS_TRPO, th32, (4, H, H, 1), 1e-6, b, 1.0 / b.B, out)
+    ops.loss_kl(L.LOSS_TRPO, th32, (4, H, H, 1), 1e-6, b, out)
     o = out.cpu().numpy()
     assert abs(o[0] + float(b.adv.double().mean())) < 1e-12 and o[1] == 0.0 and o[2] == 0.0
     g = torch.zeros(full["dims"].P, dtype=torch.float64, device=full["dev"])
     out2 = torch.zeros(3, dtype=torch.float64, device=full["dev"])
-    ops.grad(L.LOSS_TRPO, th32, (4, H, H, 1), 1e-6, b, 1.0 / b.B, g, out2)
+    ops.grad(L.LOSS_TRPO, th32, (4, H, H, 1), 1e-6, b, g, out2)
     assert abs(float(out2[0]) - o[0]) < 1e-12 and float(out2[1]) == 0.0
 
 
@@ -90,7 +90,7 @@ def test_fvp_is_linear_symmetric_and_positive(full):
 
     def F(v):
         out = torch.zeros(Pn, dtype=torch.float64, device=dev)
-        ops.fvp(th32, (4, H, H, 1), 1e-6, b, v, 1.0 / b.B, 1e-5, 1.0, out)
+        ops.fvp(th32, (4, H, H, 1), 1e-6, b, v, 1e-5, 1.0, out)
         return out
     Fx, Fy = F(x), F(y)
     z = (0.5 * x - 2.0 * y)
@@ -110,7 +110,7 @@ def test_gradient_matches_directional_derivative_of_the_loss(full):
     Pn = full["dims"].P
     dd = (4, H, H, 1)
     g = torch.zeros(Pn, dtype=torch.float64, device=dev)
-    ops.grad(L.LOSS_VPG, th32, dd, 1e-6, b, 1.0 / b.B, g)
+    ops.grad(L.LOSS_VPG, th32, dd, 1e-6, b, g)
     d = torch.tensor(np.random.RandomState(3).randn(Pn), dtype=torch.float64, device=dev)
     d = d / d.norm()
     out = torch.zeros(3, dtype=torch.float64, device=dev)
@@ -118,7 +118,7 @@ def test_gradient_matches_directional_derivative_of_the_loss(full):
     vals = []
     for sgn in (+1.0, -1.0):
         thp = (th32.double() + sgn * eps * d).float()
-        ops.loss_kl(L.LOSS_VPG, thp, dd, 1e-6, b, 1.0 / b.B, out)
+        ops.loss_kl(L.LOSS_VPG, thp, dd, 1e-6, b, out)
         vals.append(float(out[0]))
     fd = (vals[0] - vals[1]) / (2 * eps)
     assert abs(fd - float(g @ d)) < 2e-3 * abs(float(g @ d)) + 1e-6, (fd, float(g @ d))

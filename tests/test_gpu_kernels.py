@@ -174,8 +174,9 @@ def test_rollout_replay_index_work_exact(dev, env_name):
         o = env32.obs(s)
         s2, r, d = env32.step(s, env32.scale_action(traj["act"][:, t]))
         plen1 = plen + 1
-        end = d | (plen1 >= mpl) | (t == T - 1)
-        fl = d.astype(np.uint8) * 1 + end.astype(np.uint8) * 2
+        whole = d | (plen1 >= mpl)
+        end = whole | (t == T - 1)
+        fl = d.astype(np.uint8) * 1 + end.astype(np.uint8) * 2 + (end & ~whole).astype(np.uint8) * 4
         if env_name == "point":
             assert np.array_equal(traj["obs"][:, t], o)
             assert np.array_equal(traj["rew"][t], r)
@@ -385,7 +386,7 @@ def _check_update_kernels(dev, env_name, hidden, N, T):
     th32 = torch.tensor(theta, dtype=torch.float32, device=dev)
     out = torch.zeros(3, dtype=torch.float64, device=dev)
     # at theta_old: likelihood ratio == 1 exactly (same canonical summation order in rollout and update kernels)
-    ops.loss_kl(L.LOSS_TRPO, th32, dd, 1e-6, b, 1.0 / B, out)
+    ops.loss_kl(L.LOSS_TRPO, th32, dd, 1e-6, b, out)
     o = out.cpu().numpy()
     assert abs(o[0] + batch["adv"].mean()) < 1e-9 and abs(o[1]) < 1e-12 and abs(o[2]) < 1e-12
     # perturbed parameters: loss / KL / gradient against the float64 oracle
@@ -394,7 +395,7 @@ def _check_update_kernels(dev, env_name, hidden, N, T):
     th2_32 = torch.tensor(th2, dtype=torch.float32, device=dev)
     th2 = th2_32.cpu().numpy().astype(np.float64)
     for kind, name in ((L.LOSS_TRPO, "trpo"), (L.LOSS_VPG, "vpg")):
-        ops.loss_kl(kind, th2_32, dd, 1e-6, b, 1.0 / B, out)
+        ops.loss_kl(kind, th2_32, dd, 1e-6, b, out)
         o = out.cpu().numpy()
         ref_loss = P.surr_loss_trpo(th2, batch, dims) if name == "trpo" else P.surr_loss_vpg(th2, batch, dims)
         mkl, xkl = P.kl_stats(th2, batch, dims)
@@ -403,7 +404,7 @@ def _check_update_kernels(dev, env_name, hidden, N, T):
         np.testing.assert_allclose(o[2], xkl, rtol=1e-4, atol=1e-8)
         g = torch.zeros(dims.P, dtype=torch.float64, device=dev)
         out_g = torch.zeros(3, dtype=torch.float64, device=dev)
-        ops.grad(kind, th2_32, dd, 1e-6, b, 1.0 / B, g, out_g)
+        ops.grad(kind, th2_32, dd, 1e-6, b, g, out_g)
         np.testing.assert_allclose(out_g.cpu().numpy(), o, rtol=1e-5, atol=1e-8)     # fused loss/KL triple
         ref_g = P.grad_surr(th2, batch, dims, name)
         np.testing.assert_allclose(g.cpu().numpy(), ref_g, rtol=2e-4, atol=2e-6 * np.abs(ref_g).max() + 1e-9)
@@ -411,13 +412,13 @@ def _check_update_kernels(dev, env_name, hidden, N, T):
     x = rng.randn(dims.P)
     xd = torch.tensor(x, dtype=torch.float64, device=dev)
     Hx = torch.zeros(dims.P, dtype=torch.float64, device=dev)
-    ops.fvp(th32, dd, 1e-6, b, xd, 1.0 / B, 1e-5, 1.0, Hx)
+    ops.fvp(th32, dd, 1e-6, b, xd, 1e-5, 1.0, Hx)
     # activation cache: the gradient pass at theta_old stores tanh outputs, the FVP reads them back -> identical result
     hc = b.hcache(hidden, hidden)
     gtmp = torch.zeros(dims.P, dtype=torch.float64, device=dev)
-    ops.grad(L.LOSS_TRPO, th32, dd, 1e-6, b, 1.0 / B, gtmp, None, hc)
+    ops.grad(L.LOSS_TRPO, th32, dd, 1e-6, b, gtmp, None, hc)
     Hx_c = torch.zeros(dims.P, dtype=torch.float64, device=dev)
-    ops.fvp(th32, dd, 1e-6, b, xd, 1.0 / B, 1e-5, 1.0, Hx_c, hc)
+    ops.fvp(th32, dd, 1e-6, b, xd, 1e-5, 1.0, Hx_c, hc)
     np.testing.assert_allclose(Hx_c.cpu().numpy(), Hx.cpu().numpy(), rtol=1e-12, atol=1e-18)
     x32 = x.astype(np.float32).astype(np.float64)          # the kernel rounds the tangent to float32
     ref_Hx = P.fvp(theta, batch, x32, dims, 0.0) + 1e-5 * x
@@ -432,7 +433,7 @@ def test_min_std_clamp_blocks_logstd_gradient(dev):
     dd = (env.O, 32, 32, env.A)
     g = torch.zeros(dims.P, dtype=torch.float64, device=dev)
     th32 = torch.tensor(th, dtype=torch.float32, device=dev)
-    ops.grad(L.LOSS_VPG, th32, dd, 1e-3, b, 1.0 / b.B, g)
+    ops.grad(L.LOSS_VPG, th32, dd, 1e-3, b, g)
     ref = P.grad_surr(th32.cpu().numpy().astype(np.float64), batch, dims, "vpg", min_std=1e-3)
     assert g.cpu().numpy()[-1] == 0.0 and ref[-1] == 0.0
     np.testing.assert_allclose(g.cpu().numpy(), ref, rtol=5e-4, atol=1e-6 * np.abs(ref).max() + 1e-9)
@@ -505,17 +506,17 @@ def test_f64_parity_kernels_match_oracle(dev, env_name, hidden):
     out = torch.zeros(3, dtype=torch.float64, device=dev)
     g = torch.zeros(dims.P, dtype=torch.float64, device=dev)
     for kind, name in ((L.LOSS_TRPO, "trpo"), (L.LOSS_VPG, "vpg")):
-        ops.update_f64(0, kind, thd, dd, 1e-6, b, None, 1.0 / B, 0.0, 0.0, None, out)
+        ops.update_f64(0, kind, thd, dd, 1e-6, b, None, 0.0, 0.0, None, out)
         ref_loss = P.surr_loss_trpo(th, batch, dims) if name == "trpo" else P.surr_loss_vpg(th, batch, dims)
         mkl, xkl = P.kl_stats(th, batch, dims)
         np.testing.assert_allclose(out.cpu().numpy(), [ref_loss, mkl, xkl], rtol=1e-9, atol=1e-13)
-        ops.update_f64(1, kind, thd, dd, 1e-6, b, None, 1.0 / B, 0.0, 0.0, g, out)
+        ops.update_f64(1, kind, thd, dd, 1e-6, b, None, 0.0, 0.0, g, out)
         ref_g = P.grad_surr(th, batch, dims, name)
         np.testing.assert_allclose(g.cpu().numpy(), ref_g, rtol=1e-8, atol=1e-12 * np.abs(ref_g).max())
     x = rng.randn(dims.P)
     xd = torch.tensor(x, dtype=torch.float64, device=dev)
     Hx = torch.zeros(dims.P, dtype=torch.float64, device=dev)
     th0 = torch.tensor(theta, dtype=torch.float64, device=dev)
-    ops.update_f64(2, L.LOSS_TRPO, th0, dd, 1e-6, b, xd, 1.0 / B, 1e-5, 1.0, Hx, None)
+    ops.update_f64(2, L.LOSS_TRPO, th0, dd, 1e-6, b, xd, 1e-5, 1.0, Hx, None)
     ref_Hx = P.fvp(theta, batch, x, dims, 1e-5)
     np.testing.assert_allclose(Hx.cpu().numpy(), ref_Hx, rtol=1e-8, atol=1e-12 * np.abs(ref_Hx).max())

@@ -88,8 +88,11 @@ def test_policy_construction_and_errors_without_gpu():
     with pytest.raises(NotImplementedError):
         normalize(CartpoleEnv(), normalize_obs=True)
     from rllab_b200.optimizers.conjugate_gradient_optimizer import ConjugateGradientOptimizer
-    with pytest.raises(NotImplementedError):
-        ConjugateGradientOptimizer(subsample_factor=0.5)
+    ConjugateGradientOptimizer(subsample_factor=0.5)            # built in round 2 (tile-granular sub-sampling)
+    with pytest.raises(ValueError):
+        ConjugateGradientOptimizer(subsample_factor=0.0)
+    with pytest.raises(TypeError):
+        ConjugateGradientOptimizer(hvp_approach="finite-difference")
 
 
 def test_logger_tabular_and_snapshot(tmp_path):
