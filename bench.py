@@ -35,6 +35,9 @@ def make_env(name):
     if name == "cartpole":
         from rllab_b200.envs.box2d.cartpole_env import CartpoleEnv
         return normalize(CartpoleEnv())
+    if name == "cartpole_swingup":
+        from rllab_b200.envs.box2d.cartpole_swingup_env import CartpoleSwingupEnv
+        return normalize(CartpoleSwingupEnv())
     if name == "pendulum":
         from rllab_b200.envs.gym_env import GymEnv
         return normalize(GymEnv("Pendulum-v0"))

@@ -45,6 +45,7 @@ extern "C" {
 #define B200RL_ENV_PENDULUM 2
 #define B200RL_ENV_SWIMMER 3
 #define B200RL_ENV_HOPPER 4
+#define B200RL_ENV_CARTPOLE_SWINGUP 5 /* rllab/envs/box2d/cartpole_swingup_env.py (same Box2D model as CartpoleEnv) */
 
 #define B200RL_NOISE_UNIFORM 0
 #define B200RL_NOISE_NORMAL 1

@@ -123,6 +123,28 @@ class CartPoleEnv(LaneEnv):
         return s2, r.astype(dt), done
 
 
+class CartPoleSwingupEnv(CartPoleEnv):
+    """rllab/envs/box2d/cartpole_swingup_env.py:15-58 on the same Box2D model (cartpole.xml.mako) = the same reduced
+    dynamics as CartPoleEnv [3P pybox2d: PARITY UNPINNED]: reset U([-1,-2,pi-1,-3],[1,2,pi+1,3]) (:27-38), done = |x| > 3
+    (:54-55), reward (post-step) -100 if done else cos(theta) (:41-51; the -1 branch needs |x| > max_reward_cart_pos = 3 =
+    max_cart_pos, i.e. done, so it never fires)."""
+    name, kind = "cartpole_swingup", 5
+
+    def reset(self, raw):
+        dt = self.dtype
+        raw = np.asarray(raw, dt)
+        lo = np.asarray([-1.0, -2.0, np.pi - 1.0, -3.0], dt).reshape(4, 1)
+        hi = np.asarray([1.0, 2.0, np.pi + 1.0, 3.0], dt).reshape(4, 1)
+        return (lo + (hi - lo) * raw).astype(dt)
+
+    def step(self, s, u):
+        dt = self.dtype
+        s2, _, _ = CartPoleEnv.step(self, s, u)
+        done = np.abs(s2[0]) > dt(3.0)
+        r = np.where(done, dt(-100.0), np.cos(s2[2])).astype(dt)
+        return s2, r, done
+
+
 class PendulumEnv(LaneEnv):
     """gym==0.7.4 Pendulum-v0 (`rllab/envs/gym_env.py:58-116` wraps it; environment.yml:52)
     [3P gym: PARITY UNPINNED].  max_speed 8, max_torque 2, dt .05, g 10, m 1, l 1.
@@ -164,6 +186,8 @@ def make(name, dtype=np.float64):
         return PointEnv(dtype)
     if name in ("cartpole", "cartpoleenv"):
         return CartPoleEnv(dtype)
+    if name in ("cartpole_swingup", "cartpoleswingupenv"):
+        return CartPoleSwingupEnv(dtype)
     if name in ("pendulum", "pendulum-v0"):
         return PendulumEnv(dtype)
     if name in ("swimmer", "hopper"):

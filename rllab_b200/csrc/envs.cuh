@@ -74,6 +74,34 @@ struct CartPoleEnvD {
   }
 };
 
+// ---------------------------------------------------------------- rllab/envs/box2d/cartpole_swingup_env.py:15-58
+// Same Box2D model (models/cartpole.xml.mako) and therefore the same reduced-coordinate dynamics as CartPoleEnvD; what
+// differs is the task: reset x, xdot, theta, thetadot ~ U([-1,-2,pi-1,-3], [1,2,pi+1,3]) (pole hanging down), done =
+// |x| > 3, reward (post-step) = -100 if done, else cos(theta) (the "-1 beyond max_reward_cart_pos" branch cannot fire:
+// max_reward_cart_pos == max_cart_pos == 3).
+struct CartPoleSwingupEnvD {
+  static constexpr int KIND = B200RL_ENV_CARTPOLE_SWINGUP, O = 4, A = 1, S = 4, K = 4, NOISE = B200RL_NOISE_UNIFORM;
+  __host__ __device__ static constexpr float lb(int) { return -10.0f; }
+  __host__ __device__ static constexpr float ub(int) { return 10.0f; }
+  __device__ static void reset(float (&s)[S], const float (&raw)[K]) {
+    const float PI = 3.14159265358979323846f;
+    const float lo[4] = {-1.0f, -2.0f, PI - 1.0f, -3.0f}, hi[4] = {1.0f, 2.0f, PI + 1.0f, 3.0f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] = lo[i] + (hi[i] - lo[i]) * raw[i];
+  }
+  __device__ static void obs(const float (&s)[S], float (&o)[O]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = s[i];
+  }
+  __device__ static void step(float (&s)[S], const float (&u)[A], float& r, bool& done) {
+    float rr;
+    bool dd;
+    CartPoleEnvD::step(s, u, rr, dd);          // shared dynamics; its reward / termination are replaced below
+    done = fabsf(s[0]) > 3.0f;
+    r = done ? -100.0f : cosf(s[2]);
+  }
+};
+
 // ---------------------------------------------------------------- gym 0.7.4 Pendulum-v0 via rllab/envs/gym_env.py:58-116
 struct PendulumEnvD {
   static constexpr int KIND = B200RL_ENV_PENDULUM, O = 3, A = 1, S = 2, K = 2, NOISE = B200RL_NOISE_UNIFORM;
@@ -125,6 +153,7 @@ namespace b200rl {
     case B200RL_ENV_POINT: { using Env = ::b200rl::PointEnvD; __VA_ARGS__; } break;           \
     case B200RL_ENV_CARTPOLE: { using Env = ::b200rl::CartPoleEnvD; __VA_ARGS__; } break;     \
     case B200RL_ENV_PENDULUM: { using Env = ::b200rl::PendulumEnvD; __VA_ARGS__; } break;     \
+    case B200RL_ENV_CARTPOLE_SWINGUP: { using Env = ::b200rl::CartPoleSwingupEnvD; __VA_ARGS__; } break; \
     B200RL_PLANAR_CASES(__VA_ARGS__)                                                          \
     default:                                                                                  \
       ::b200rl::set_error("unknown env kind %d", (int)(kind));                                \

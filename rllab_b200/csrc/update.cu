@@ -174,8 +174,10 @@ int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim
   fill_args(a, params_f32, min_std, B, obs, nullptr, nullptr, nullptr, nullptr, B200RL_LOSS_TRPO, flags, ws);
   a.xvec = x; a.h_cache = const_cast<float*>(h_cache); a.tile_list = tile_list; a.n_list = n_list;
   int grid = 0, P = 0, ols = 0;
+  // 64-wide nets with cached activations: tcgen05 kernel (update_umma.cu); without a cache the FP32 tiled-GEMM kernel
   int rc = (h1 == 32) ? update_tile_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st)
-                      : update_gemm_launch(MODE_FVP, obs_dim, h1, act_dim, a, &grid, &P, &ols, st);
+           : (h_cache != nullptr) ? update_umma_fvp_launch(obs_dim, act_dim, a, &grid, &P, &ols, st)
+                                  : update_gemm_launch(MODE_FVP, obs_dim, h1, act_dim, a, &grid, &P, &ols, st);
   if (rc) return rc;
   FinArgs f{};
   f.partial = ws; f.nblocks = grid; f.K = P; f.vec_out = Hx_out; f.tri_out = nullptr;

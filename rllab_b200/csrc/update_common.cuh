@@ -46,4 +46,8 @@ int update_gemm_launch(int mode, int obs_dim, int h, int act_dim, const UpdArgs&
                        int* ols_out, cudaStream_t st);
 
 
+// 64-wide nets, Fisher-vector product with cached activations: dense layer chain on the tensor cores (update_umma.cu)
+int update_umma_fvp_launch(int obs_dim, int act_dim, const UpdArgs& a, int* grid_out, int* P_out, int* ols_out,
+                           cudaStream_t st);
+
 }  // namespace b200rl

@@ -33,7 +33,7 @@ def _L():
     return _lib
 
 
-ENVS = ["point", "cartpole", "pendulum"]
+ENVS = ["point", "cartpole", "pendulum", "cartpole_swingup"]
 try:
     from oracle import planar as _planar      # noqa: F401
     ENVS += ["swimmer", "hopper"]
