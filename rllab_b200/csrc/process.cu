@@ -11,12 +11,28 @@ namespace b200rl {
 constexpr int OMAX = 32;  // max obs_dim handled by the runtime-O feature code
 
 // LinearFeatureBaseline features . w  (linear_feature_baseline.py:19-23): [clip(o,+-10), o^2, al, al^2, al^3, 1]
-__device__ __forceinline__ double lfb_predict(const float* __restrict__ obs, size_t plane, size_t idx, int O,
+// OT > 0: compile-time obs_dim -- the O loads of a step are issued back to back (and, with the caller's step loop
+// unrolled, hoisted across steps) instead of one load -> use chain per feature (in-order issue stalls at the first use of
+// every load: the runtime-O loop exposed 8 x O serial DRAM latencies per window -- 0.55 ms on cfg2, round 2 measurement)
+template <int OT>
+__device__ __forceinline__ double lfb_predict(const float* __restrict__ obs, size_t plane, size_t idx, int O_rt,
                                               unsigned short ts, const double* __restrict__ w) {
   double acc = 0.0;
-  for (int k = 0; k < O; ++k) {
-    double o = (double)fminf(fmaxf(obs[k * plane + idx], -10.0f), 10.0f);
-    acc += o * w[k] + (o * o) * w[O + k];
+  const int O = OT > 0 ? OT : O_rt;
+  if constexpr (OT > 0) {
+    float ov[OT];
+#pragma unroll
+    for (int k = 0; k < OT; ++k) ov[k] = obs[k * plane + idx];
+#pragma unroll
+    for (int k = 0; k < OT; ++k) {
+      const double o = (double)fminf(fmaxf(ov[k], -10.0f), 10.0f);
+      acc += o * w[k] + (o * o) * w[OT + k];
+    }
+  } else {
+    for (int k = 0; k < O; ++k) {
+      double o = (double)fminf(fmaxf(obs[k * plane + idx], -10.0f), 10.0f);
+      acc += o * w[k] + (o * o) * w[O + k];
+    }
   }
   double al = (double)ts / 100.0;
   acc += al * w[2 * O] + (al * al) * w[2 * O + 1] + (al * al * al) * w[2 * O + 2] + w[2 * O + 3];
@@ -45,6 +61,7 @@ __device__ __forceinline__ double lfb_predict(const float* __restrict__ obs, siz
 // every statistic (count, path counts, returns); downstream kernels skip masked samples.
 constexpr int PS_L = 8, PS_WARPS = 8, PS_THREADS2 = 32 * PS_WARPS, PS_WIN = PS_L * PS_WARPS;
 
+template <int OT>
 __global__ void __launch_bounds__(PS_THREADS2, 2)
     process_samples_kernel(int O, int N, int T, const float* __restrict__ obs, const float* __restrict__ rew,
                            unsigned char* __restrict__ flags, const unsigned short* __restrict__ tstep,
@@ -97,7 +114,7 @@ __global__ void __launch_bounds__(PS_THREADS2, 2)
       endm |= (unsigned)((f & B200RL_FLAG_END) ? 1 : 0) << u;
       cutm |= (unsigned)((f & B200RL_FLAG_CUT) ? 1 : 0) << u;
       startm |= (unsigned)(ts == 0 ? 1 : 0) << u;
-      bs[u] = (have_w && act) ? lfb_predict(obs, plane, idx, O, ts, sw) : 0.0;
+      bs[u] = (have_w && act) ? lfb_predict<OT>(obs, plane, idx, O, ts, sw) : 0.0;
       if (act) base[idx] = (float)bs[u];
     }
     if (!drop_cut) cutm = 0;
@@ -364,9 +381,19 @@ int b200rl_process_samples(int obs_dim, int N, int T, const float* obs, const fl
   double* psum = ws;
   double* pmax = ws + (size_t)grid * B200RL_PS_NSUM;
   B200RL_REQUIRE((long long)grid * (B200RL_PS_NSUM + B200RL_PS_NMAX) <= b200rl_ws_doubles(), "workspace too small");
-  process_samples_kernel<<<grid, PS_THREADS2, 0, st>>>(obs_dim, N, T, obs, rew, flags, tstep, w, discount,
-                                                       discount * gae_lambda, drop_cut_paths, adv, ret, base, psum,
-                                                       pmax);
+#define B200RL_PS_LAUNCH(OT)                                                                                     \
+  process_samples_kernel<OT><<<grid, PS_THREADS2, 0, st>>>(obs_dim, N, T, obs, rew, flags, tstep, w, discount,        \
+                                                           discount * gae_lambda, drop_cut_paths, adv, ret, base, psum, \
+                                                           pmax)
+  switch (obs_dim) {                 // the obs dims of the compiled envs get an unrolled baseline predictor
+    case 2: B200RL_PS_LAUNCH(2); break;
+    case 3: B200RL_PS_LAUNCH(3); break;
+    case 4: B200RL_PS_LAUNCH(4); break;
+    case 13: B200RL_PS_LAUNCH(13); break;
+    case 20: B200RL_PS_LAUNCH(20); break;
+    default: B200RL_PS_LAUNCH(0); break;
+  }
+#undef B200RL_PS_LAUNCH
   B200RL_LAUNCH_CHECK("process_samples_kernel");
   int rc = launch_finalize_sum(psum, grid, B200RL_PS_NSUM, sums_out, 1.0, st);
   if (rc) return rc;
@@ -412,7 +439,8 @@ int b200rl_lfb_gram(int obs_dim, long long B, const float* obs, const unsigned s
     B200RL_LAUNCH_CHECK("lfb_gram_reg_kernel");
     return launch_finalize_sum(ws, grid, npairs, gram_out, 1.0, st);
   }
-  B200RL_SET_MAX_SMEM(lfb_gram_kernel, smem);
+  // smem <= 45 rows x 528 B = 23.8 KB: below the default 48 KB dynamic limit, no attribute needed (and a per-kernel
+  // attribute set for a small obs_dim would cap a later, larger one)
   lfb_gram_kernel<<<grid, GRAM_THREADS, smem, st>>>(obs_dim, B, obs, tstep, ret, flags, ws);
   B200RL_LAUNCH_CHECK("lfb_gram_kernel");
   return launch_finalize_sum(ws, grid, npairs, gram_out, 1.0, st);

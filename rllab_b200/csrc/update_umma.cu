@@ -216,9 +216,10 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) gW1[r][c] = make_float2(0.f, 0.f);
-  // small outputs: threads [0, 128): (dW0[o-half][:, j], and for half 0 db0[j]) with j = tid % 64; threads [128, 192): db1[j]
-  constexpr int OH = (O + 1) / 2;
-  const int sj = tid & 63, soh = (tid >> 6) & 1;
+  // small outputs, all 256 threads: thread (j = tid % 64, quarter = tid / 64) owns dW0[o][j] for the quarter's obs rows;
+  // quarter 0 also sums db0[j] (the D1 row it streams anyway), quarter 1 db1[j] (one extra row)
+  constexpr int OH = (O + 3) / 4;
+  const int sj = tid & 63, soh = tid >> 6;
   float2 gS[OH + 1];
 #pragma unroll
   for (int k = 0; k <= OH; ++k) gS[k] = make_float2(0.f, 0.f);
@@ -246,22 +247,21 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
           gW1[r][c] = make_float2(0.f, 0.f);
         }
     }
-    if (tid < 2 * H) {
+    {
       double t[OH + 1];
 #pragma unroll
       for (int oo = 0; oo < OH; ++oo) {
         const int o = soh * OH + oo;
         t[oo] = o < O ? out[N::oW0 + o * H + sj] : 0.0;
       }
-      t[OH] = out[N::ob0 + sj];
+      t[OH] = soh == 0 ? out[N::ob0 + sj] : (soh == 1 ? out[N::ob1 + sj] : 0.0);
 #pragma unroll
       for (int oo = 0; oo < OH; ++oo) {
         const int o = soh * OH + oo;
         if (o < O) out[N::oW0 + o * H + sj] = t[oo] + (double)(gS[oo].x + gS[oo].y);
       }
       if (soh == 0) out[N::ob0 + sj] = t[OH] + (double)(gS[OH].x + gS[OH].y);
-    } else if (tid < 3 * H) {
-      out[N::ob1 + sj] += (double)(gS[0].x + gS[0].y);
+      if (soh == 1) out[N::ob1 + sj] = t[OH] + (double)(gS[OH].x + gS[OH].y);
     }
 #pragma unroll
     for (int k = 0; k <= OH; ++k) gS[k] = make_float2(0.f, 0.f);
@@ -489,6 +489,26 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
     __syncthreads();
     // ================= H: Gram products over the tile (FP32 pipe)
     {
+      // while the FP32 pipe works on this tile, pull the next tile's rows into L2 (its loads are otherwise fully exposed)
+      const long long nti = ti_ + gridDim.x;
+      if (nti < ntiles) {
+        const long long ns = tile_at(a, nti) * U_TILE + q * 32;      // one 128 B line per (row, warp): lane 0 fetches it
+        if (lane == 0 && ns < a.B) {
+          const float* hcn = a.h_cache + ns;
+#pragma unroll 8
+          for (int c = 0; c < 32; ++c) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(hcn + (size_t)(j0 + c) * a.B));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(hcn + (size_t)(H + j0 + c) * a.B));
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int o = hf * 16 + c;
+            if (o < O) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.obs + (size_t)o * a.B + ns));
+          }
+        }
+      }
+    }
+    {
       const float* Ur = stage + (SM::rH1 + ti) * LD;
       const float* Vr = stage + (SM::rD2 + tj) * LD;
 #pragma unroll 2
@@ -500,8 +520,9 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
         for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(Vr + c * 16 * LD + k);
         gram_4x4(u, v, gW1);
       }
-      if (tid < 2 * H) {                       // dW0[o-half][:, sj] (+ db0[sj] in half 0)
+      {
         const float* Dr = stage + (SM::rD1 + sj) * LD;
+        const float* D2r = stage + (SM::rD2 + sj) * LD;
 #pragma unroll 2
         for (int k = 0; k < U_TILE; k += 4) {
           const float4 d = *reinterpret_cast<const float4*>(Dr + k);
@@ -513,14 +534,11 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
               gram_fma4(xv, d, gS[oo]);
             }
           }
-          gS[OH].x += (d.x + d.y) + (d.z + d.w);
-        }
-      } else if (tid < 3 * H) {                // db1[sj]
-        const float* Dr = stage + (SM::rD2 + sj) * LD;
-#pragma unroll 2
-        for (int k = 0; k < U_TILE; k += 4) {
-          const float4 d = *reinterpret_cast<const float4*>(Dr + k);
-          gS[0].x += (d.x + d.y) + (d.z + d.w);
+          if (soh == 0) gS[OH].x += (d.x + d.y) + (d.z + d.w);
+          if (soh == 1) {
+            const float4 e = *reinterpret_cast<const float4*>(D2r + k);
+            gS[OH].x += (e.x + e.y) + (e.z + e.w);
+          }
         }
       }
     }

@@ -34,7 +34,7 @@ def dev():
 
 
 # ------------------------------------------------------------------------------------------- process_samples
-@pytest.mark.parametrize("N,T,mpl", [(1, 1, 1), (33, 7, 3), (200, 64, 64), (70, 65, 20), (257, 130, 41), (40, 500, 500),
+@pytest.mark.parametrize("N,T,mpl", [(1, 5, 3), (33, 7, 3), (200, 64, 64), (70, 65, 20), (257, 130, 41), (40, 500, 500),
                                      (96, 129, 500)])
 @pytest.mark.parametrize("drop", [False, True])
 def test_process_samples_scan_shapes(dev, N, T, mpl, drop):
@@ -77,7 +77,8 @@ def test_whole_paths_masking_through_update_passes(dev):
         ref = S.process_samples_lanes(traj, None, 0.99, 1.0, center_adv=True, drop_cut=True)
         valid = ref["valid"]
         assert 0.02 < (~valid).mean() < 0.9                                  # the case has a real share of cut paths
-        batch = S.batch_from_traj(traj, ref["adv"], valid)
+        np.testing.assert_allclose(b.adv.cpu().numpy(), ref["adv"], rtol=1e-4, atol=2e-5)
+        batch = S.batch_from_traj(traj, b.adv.cpu().numpy(), valid)      # the device's own (float32) advantages
         d1 = 2 * b.O + 5
         ops.lfb_gram(b, b.gram)
         F = S.lfb_features_lanes(traj["obs"], traj["tstep"]).reshape(d1 - 1, -1)
