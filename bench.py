@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short TRPO workloads reported under extra.workloads")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-arm-json", action="store_true", help=argparse.SUPPRESS)   # internal: CPU leg in a clean process
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
     rank = int(os.environ.get("RANK", "0"))
@@ -158,6 +159,12 @@ def main():
     lanes = args.lanes or lanes
     T = args.horizon or T
 
+    if args.cpu_arm_json:
+        # the cpu_baseline leg of the default run, executed in a fresh interpreter: its worker pool forks, and a fork
+        # of a process that has initialised CUDA dies in the children as soon as one of them frees a device object
+        _, info, _ = cpu_arm(args.workload, 2, 1, seconds_budget=args.cpu_seconds)
+        print(json.dumps(info))
+        return
     if args.impl == "reference":
         if rank != 0:
             return
@@ -422,8 +429,13 @@ def main():
         # worth timing; the CPU baseline is reported for the classic-control workloads only.
         line["cpu_baseline"] = None
     elif world == 1 and not args.no_cpu_baseline:
-        _, info, _ = cpu_arm(args.workload, 2, 1, seconds_budget=args.cpu_seconds)
-        line["cpu_baseline"] = info
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-arm-json", "--workload", args.workload,
+                                  "--cpu-seconds", str(args.cpu_seconds)], capture_output=True, text=True, timeout=600,
+                                 env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+            line["cpu_baseline"] = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as exc:                                            # noqa: BLE001
+            line["cpu_baseline"] = dict(value=None, unit="env-steps/s", kind="port", error=repr(exc)[:200])
     print(json.dumps(line))
     comm.close()
 
