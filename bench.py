@@ -247,10 +247,11 @@ def main():
     run(algo, policy, args.warmup, itr, False)
     itr += args.warmup
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    k0, c0 = L.kernel_launches(), comm.n_collectives
+    k0, c0, x0 = L.kernel_launches(), comm.n_collectives, comm.n_peer_exchanges
     ms_dev = run(algo, policy, args.steps, itr, False)
     launches = (L.kernel_launches() - k0) / args.steps
-    collectives = (comm.n_collectives - c0) / args.steps
+    collectives = (comm.n_collectives - c0) / args.steps            # NCCL collectives on the iteration's critical path
+    peer_exchanges = (comm.n_peer_exchanges - x0) / args.steps      # peer-memory exchanges (fused or stand-alone kernels)
     itr += args.steps
     d2h0 = ops.PendingHost.bytes_total
     ms_e2e = run(algo, policy, args.steps, itr, True)
@@ -276,6 +277,7 @@ def main():
             def __init__(self):
                 self.world_size, self.rank, self.local_rank, self.active = 1, 0, local_rank, False
                 self._gather_bufs, self.n_collectives, self._owns_group = {}, 0, False
+                self.peer, self.n_peer_exchanges, self._windows = False, 0, None
         small = "cartpole_vpg_65536x200"
         a_sh, p_sh, _, _ = build(small, 1024, 50, comm, seed=5)
         a_solo, p_solo, _, _ = build(small, 1024 * world, 50, _Solo(), seed=5)
@@ -415,7 +417,10 @@ def main():
                     l2="trajectory buffers (%.0f MB/GPU) exceed the 126 MB L2" % (b.B * (alg_bytes + 14) / 1e6)),
         e2e=dict(value=e2e_value, unit="env-steps/s", ms_per_step=ms_e2e / args.steps,
                  h2d_bytes_per_step=8 * P_, d2h_bytes_per_step=8 * P_ + d2h_stats),
-        gpu_launches=launches, collectives_per_step=collectives, clocks=clk, roofline=roofline,
+        gpu_launches=launches, collectives_per_step=collectives, peer_exchanges_per_step=peer_exchanges,
+        transport=("peer-memory windows over NVLink (csrc/peer.cuh)" if comm.peer else
+                   ("NCCL all-gather + rank-order fold" if comm.active else "single GPU")),
+        clocks=clk, roofline=roofline,
         roofline_hbm=roofline_hbm, fp32_peak_tflops=fp32_peak,
         kernels={k: dict(ms=round(v["ms"], 4), GBps=round(v["GBps"], 1), TFLOPs=round(v["TFLOPs"], 2), bound=v["bound"],
                          frac=round(v["frac"], 4), per_iter=v["per_iter"], share_of_step=round(v["share_of_step"], 3))

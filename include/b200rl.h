@@ -232,6 +232,28 @@ int b200rl_f64_to_f32(long long n, const double* src, float* dst, void* stream);
  * rank's vector) -> out[i] = sum over ranks for i < n_sum, max over ranks for i >= n_sum, in rank order. */
 int b200rl_reduce_ranks(const double* gathered, int world, long long n, long long n_sum, double* out, void* stream);
 
+/* ---- peer-memory collectives over NVLink / NVSwitch (the reference's update is single-process, it has
+ * no counterpart).  One process per GPU.  Every rank creates an exchange window in its own HBM, the IPC handles are
+ * swapped by the host (torch.distributed / any rendezvous), every rank maps all peers' windows and binds the table.
+ * A collective is ONE kernel per rank: push the vector into every window, signal, wait for all peers, fold the `world`
+ * copies in rank order (bit-identical results on all ranks).  See rllab_b200/csrc/peer.cuh. */
+#define B200RL_PEER_MAX_RANKS 16
+#define B200RL_IPC_HANDLE_BYTES 64
+long long b200rl_peer_window_bytes(int world, long long n_cap);
+/* window of `world` x 2 slots of n_cap float64 (+ flags), zeroed; handle_out [B200RL_IPC_HANDLE_BYTES] */
+int b200rl_peer_window_create(int world, long long n_cap, void** window_out, unsigned char* handle_out);
+int b200rl_peer_window_open(const unsigned char* handle, void** window_out);    /* map a peer's window */
+int b200rl_peer_window_close(void* window);                                      /* unmap a peer's window */
+int b200rl_peer_window_destroy(void* window);                                    /* free the own window */
+/* windows [world]: device base pointers indexed by rank (entry `rank` = own window); NULL / world <= 1 unbinds */
+int b200rl_peer_bind(void* const* windows, int rank, int world, long long n_cap);
+/* in place: t[i] = sum over ranks (i < n_sum) | max over ranks (i >= n_sum); n <= n_cap */
+int b200rl_peer_allreduce_mixed(double* t, long long n, long long n_sum, void* stream);
+/* enable != 0: until switched off again, b200rl_loss_kl / b200rl_grad / b200rl_fvp / b200rl_update_f64 deliver results
+ * reduced over ALL ranks -- the exchange is fused into the finalize kernel of the pass (one launch: fold the per-block
+ * partials, push into the peers' windows, fold over ranks).  Every rank must issue the same sequence of calls. */
+int b200rl_peer_fuse_updates(int enable);
+
 /* (T,N)-planar lane layout <-> the reference's sample-major (B, dim) float64 wire format
  * (samples_data["observations"] etc., rllab/sampler/base.py:74-104): dst[(t*N+n)*dim + k] = src[k][t][n]. */
 int b200rl_planes_to_rows_f64(int dim, long long B, const float* src, double* dst, void* stream);

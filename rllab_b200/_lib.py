@@ -60,6 +60,14 @@ SIGNATURES = {
     "b200rl_axpy_params": (c_int, [_LL, _P, _P, c_double, _P, _P, _P]),
     "b200rl_adam_step": (c_int, [_LL, _P, _P, _P, _P, _P, _LL, c_double, c_double, c_double, c_double, _P]),
     "b200rl_f64_to_f32": (c_int, [_LL, _P, _P, _P]),
+    "b200rl_peer_window_bytes": (_LL, [c_int, _LL]),
+    "b200rl_peer_window_create": (c_int, [c_int, _LL, POINTER(c_void_p), _P]),
+    "b200rl_peer_window_open": (c_int, [_P, POINTER(c_void_p)]),
+    "b200rl_peer_window_close": (c_int, [_P]),
+    "b200rl_peer_window_destroy": (c_int, [_P]),
+    "b200rl_peer_bind": (c_int, [_P, c_int, c_int, _LL]),
+    "b200rl_peer_allreduce_mixed": (c_int, [_P, _LL, _LL, _P]),
+    "b200rl_peer_fuse_updates": (c_int, [c_int]),
     "b200rl_reduce_ranks": (c_int, [_P, c_int, _LL, _LL, _P, _P]),
     "b200rl_planes_to_rows_f64": (c_int, [c_int, _LL, _P, _P, _P]),
 }

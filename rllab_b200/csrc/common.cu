@@ -1,7 +1,7 @@
 // Error plumbing, device queries and the fixed-order finalize kernels shared by every reduction.
 #include <stdarg.h>
 
-#include "common.cuh"
+#include "peer.cuh"
 
 namespace b200rl {
 
@@ -70,13 +70,24 @@ int launch_finalize_max(const double* partial, int nblocks, int K, double* out, 
   return 0;
 }
 
-// see common.cuh: blocks [0, ceil(K/32)) reduce the vector, one extra block reduces the loss/KL tuple
+// see common.cuh: blocks [0, ceil(K/32)) reduce the vector, one extra block reduces the loss/KL tuple.  With a peer
+// communicator (f.peer.world > 1) every block pushes its outputs into slot[rank] of all exchange windows instead of
+// writing them out, the last block to finish signals the peers, and every block then folds the `world` slots of the own
+// window in rank order (peer.cuh) -- the reduction over blocks and the all-reduce over GPUs are one launch.
 __global__ void __launch_bounds__(256) finalize_update_kernel(FinArgs f) {
   __shared__ double sm[8][33];
+  __shared__ int sh_last, sh_ok;
   const int kx = threadIdx.x & 31, by = threadIdx.x >> 5;
   const double sc = f.scale / (f.count != nullptr ? f.count[0] : 1.0);
   const int nvb = (f.K + 31) / 32;
-  if ((int)blockIdx.x < nvb) {
+  const bool is_vec = (int)blockIdx.x < nvb;
+  const bool peered = f.peer.world > 1;
+  const int par = (int)(f.peer.seq & 1ull);
+  // index of this thread's output in the exchanged message [vector | tuple], -1: none
+  long long slot_i = -1;
+  bool is_max = false;
+  double r = 0.0;
+  if (is_vec) {
     const int k = blockIdx.x * 32 + kx;
     double acc = 0.0;
     if (k < f.K) {
@@ -86,7 +97,7 @@ __global__ void __launch_bounds__(256) finalize_update_kernel(FinArgs f) {
     sm[by][kx] = acc;
     __syncthreads();
     if (by == 0 && k < f.K) {
-      double r = sm[0][kx];
+      r = sm[0][kx];
 #pragma unroll
       for (int y = 1; y < 8; ++y) r += sm[y][kx];
       r *= sc;
@@ -94,23 +105,24 @@ __global__ void __launch_bounds__(256) finalize_update_kernel(FinArgs f) {
       if (f.post == FIN_GRAD) {
         // TT.maximum routes the gradient to the constant where the min_std clamp is active (gaussian_mlp_policy.py:100)
         if (is_ls) {
-          const double par = f.params64 ? f.params64[k] : (double)f.params32[k];
-          if (!(par > f.log_min_std)) r = 0.0;
+          const double par_k = f.params64 ? f.params64[k] : (double)f.params32[k];
+          if (!(par_k > f.log_min_std)) r = 0.0;
         }
       } else if (f.post == FIN_FVP) {
         // the log_std slot of the sample sum is zero (the mean does not depend on log_std): reg * x and the M_l block
         double add = f.reg * f.x[k];
         if (is_ls) {
-          const double par = f.params64 ? f.params64[k] : (double)f.params32[k];
+          const double par_k = f.params64 ? f.params64[k] : (double)f.params32[k];
           r = 0.0;
-          if (par > f.log_min_std) {
-            const double s = exp(2.0 * par), eps = 1e-8;
+          if (par_k > f.log_min_std) {
+            const double s = exp(2.0 * par_k), eps = 1e-8;
             add += 4.0 * s * (2.0 * s - eps) / ((2.0 * s + eps) * (2.0 * s + eps)) * f.x[k];
           }
         }
         r += f.diag_scale * add;
       }
-      f.vec_out[k] = r;
+      slot_i = k;
+      if (!peered) f.vec_out[k] = r;
     }
   } else if (f.tri_out != nullptr) {
     // tuple: entries [0, NT-1) are sums, entry NT-1 is a max; thread (by, kx): kx < NT handles column kx
@@ -124,11 +136,43 @@ __global__ void __launch_bounds__(256) finalize_update_kernel(FinArgs f) {
     sm[by][kx] = acc;
     __syncthreads();
     if (by == 0 && kx < f.NT) {
-      double r = sm[0][kx];
+      r = sm[0][kx];
+      is_max = (kx == f.NT - 1);
 #pragma unroll
-      for (int y = 1; y < 8; ++y) r = (kx == f.NT - 1) ? fmax(r, sm[y][kx]) : r + sm[y][kx];
-      f.tri_out[kx] = (kx == f.NT - 1) ? r : r * sc;
+      for (int y = 1; y < 8; ++y) r = is_max ? fmax(r, sm[y][kx]) : r + sm[y][kx];
+      if (!is_max) r *= sc;
+      slot_i = f.K + kx;
+      if (!peered) f.tri_out[kx] = r;
     }
+  }
+  if (!peered) return;
+  // ---- exchange over the peer windows
+  if (slot_i >= 0)
+    for (int w = 0; w < f.peer.world; ++w) peer_slot(f.peer, w, par, f.peer.rank)[slot_i] = r;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sh_ok = 1;
+    unsigned int* cnt = peer_done_counter(f.peer.win[f.peer.rank]);
+    const unsigned int prev = atomicAdd(cnt, 1u);
+    sh_last = (prev == gridDim.x - 1) ? 1 : 0;
+    if (sh_last) {
+      *cnt = 0u;                 // every block has counted: ready for the next collective (next launch on this stream)
+      __threadfence_system();
+    }
+  }
+  __syncthreads();
+  if (sh_last && (int)threadIdx.x < f.peer.world) peer_signal(f.peer, threadIdx.x);
+  if ((int)threadIdx.x < f.peer.world && !peer_wait(f.peer, threadIdx.x)) sh_ok = 0;
+  __syncthreads();
+  if (slot_i >= 0) {
+    double acc = peer_slot(f.peer, f.peer.rank, par, 0)[slot_i];
+    for (int w = 1; w < f.peer.world; ++w) {
+      const double v = peer_slot(f.peer, f.peer.rank, par, w)[slot_i];
+      acc = is_max ? fmax(acc, v) : acc + v;
+    }
+    if (!sh_ok) acc = __longlong_as_double(0x7FF8000000000000ll);    // a peer never arrived: poison
+    if (is_vec) f.vec_out[slot_i] = acc; else f.tri_out[slot_i - f.K] = acc;
   }
 }
 

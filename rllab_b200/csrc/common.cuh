@@ -178,7 +178,18 @@ int launch_finalize_max(const double* partial, int nblocks, int K, double* out, 
 // The count is read from DEVICE memory (the all-reduced number of valid samples, sums[2] of b200rl_process_samples):
 // with whole-path masking the divisor of every mean is only known on the device, and reading it there keeps the
 // iteration free of host synchronisation.
+//   peer.world > 1   : the vector and the tuple are additionally reduced over the ranks of the bound peer-memory
+//                      communicator in the same launch (peer.cuh): sums (and the tuple's max) of every rank's result
 constexpr int FIN_NONE = 0, FIN_GRAD = 1, FIN_FVP = 2;
+constexpr int PEER_MAX_RANKS = B200RL_PEER_MAX_RANKS;
+struct PeerArgs {
+  unsigned char* win[PEER_MAX_RANKS];   // exchange-window base pointers, indexed by rank (entry `rank` = own window)
+  int rank, world;                      // world <= 1: no exchange
+  long long n_cap;                      // doubles per slot
+  unsigned long long seq;               // 1-based sequence number of this collective (identical on all ranks)
+};
+bool peer_fused();                      // a communicator is bound and fusion into the update passes is enabled
+PeerArgs peer_next();                   // arguments of the next collective (consumes one sequence number)
 struct FinArgs {
   const double* partial; int nblocks; int K; double* vec_out;
   const double* tri_partial; int NT; double* tri_out;
@@ -186,6 +197,7 @@ struct FinArgs {
   int post, ols, A;
   const float* params32; const double* params64; double log_min_std;
   const double* x; double reg, diag_scale;
+  PeerArgs peer;
 };
 int launch_finalize_update(const FinArgs& f, cudaStream_t s);
 

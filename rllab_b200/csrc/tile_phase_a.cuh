@@ -4,14 +4,9 @@
 // one dense-layer accumulator set (64) are live at any time (~110 registers + constants).  ptxas' allocation for the
 // fully unrolled fused body is otherwise erratic (it picked 72..255 registers with up to 9 KB of spills).
 #pragma once
-#include "update_common.cuh"
+#include "tile_gram.cuh"
 
 namespace b200rl {
-
-struct TileDist {  // per-kernel distribution constants (A <= 3)
-  float ls_new[3], inv_std[3], ls_old[3], inv_std_old[3], Mmu[3], var_new[3], var_new2[3], var_old[3];
-  float sum_ls_new, sum_ls_old, half_log2pi_A;
-};
 
 #define B200RL_SECTION_BARRIER() asm volatile("" ::: "memory")  // keep smem weights from staying live in registers
 

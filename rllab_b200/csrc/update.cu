@@ -135,6 +135,7 @@ int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, 
   FinArgs f{};
   f.partial = nullptr; f.nblocks = grid; f.K = 0; f.vec_out = nullptr;
   f.tri_partial = ws; f.NT = 3; f.tri_out = out; f.scale = scale; f.count = count; f.post = FIN_NONE;
+  if (peer_fused()) f.peer = peer_next();
   return launch_finalize_update(f, st);
 }
 
@@ -151,7 +152,11 @@ int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int
   fill_args(a, params_f32, min_std, B, obs, act, adv, old_mean, old_log_std, loss_kind, flags, ws);
   a.h_cache = h_cache_out;
   int grid = 0, P = 0, ols = 0;
+#ifdef B200RL_AB_TILE32
   int rc = (h1 == 32) ? update_tile_launch(MODE_GRAD, obs_dim, act_dim, a, &grid, &P, &ols, st)
+#else
+  int rc = (h1 == 32) ? update_umma32_launch(MODE_GRAD, obs_dim, act_dim, a, &grid, &P, &ols, st)
+#endif
                       : update_gemm_launch(MODE_GRAD, obs_dim, h1, act_dim, a, &grid, &P, &ols, st);
   if (rc) return rc;
   FinArgs f{};
@@ -159,6 +164,7 @@ int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int
   f.tri_partial = ws + (size_t)grid * P; f.NT = 3; f.tri_out = loss_out;   // per-block triples follow the [grid][P] partials
   f.scale = scale; f.count = count; f.post = FIN_GRAD; f.ols = ols; f.A = act_dim;
   f.params32 = params_f32; f.log_min_std = (double)a.log_min_std;
+  if (peer_fused()) f.peer = peer_next();
   return launch_finalize_update(f, st);
 }
 
@@ -175,7 +181,13 @@ int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim
   a.xvec = x; a.h_cache = const_cast<float*>(h_cache); a.tile_list = tile_list; a.n_list = n_list;
   int grid = 0, P = 0, ols = 0;
   // 64-wide nets with cached activations: tcgen05 kernel (update_umma.cu); without a cache the FP32 tiled-GEMM kernel
+  // 32-wide nets with cached activations: tcgen05 kernel (update_umma32.cu); without a cache the FP32 tile kernel
+#ifdef B200RL_AB_TILE32
   int rc = (h1 == 32) ? update_tile_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st)
+#else
+  int rc = (h1 == 32) ? ((h_cache != nullptr) ? update_umma32_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st)
+                                              : update_tile_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st))
+#endif
            : (h_cache != nullptr) ? update_umma_fvp_launch(obs_dim, act_dim, a, &grid, &P, &ols, st)
                                   : update_gemm_launch(MODE_FVP, obs_dim, h1, act_dim, a, &grid, &P, &ols, st);
   if (rc) return rc;
@@ -183,6 +195,7 @@ int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim
   f.partial = ws; f.nblocks = grid; f.K = P; f.vec_out = Hx_out; f.tri_out = nullptr;
   f.scale = scale; f.count = count; f.post = FIN_FVP; f.ols = ols; f.A = act_dim;
   f.params32 = params_f32; f.log_min_std = (double)a.log_min_std; f.x = x; f.reg = reg_coeff; f.diag_scale = diag_scale;
+  if (peer_fused()) f.peer = peer_next();
   return launch_finalize_update(f, st);
 }
 

@@ -50,4 +50,10 @@ int update_gemm_launch(int mode, int obs_dim, int h, int act_dim, const UpdArgs&
 int update_umma_fvp_launch(int obs_dim, int act_dim, const UpdArgs& a, int* grid_out, int* P_out, int* ols_out,
                            cudaStream_t st);
 
+
+// 32-wide nets, gradient and (with cached activations) Fisher-vector product: dense layer chain on the tensor cores
+// (update_umma32.cu); same contract as update_tile_launch.
+int update_umma32_launch(int mode, int obs_dim, int act_dim, const UpdArgs& a, int* grid_out, int* P_out, int* ols_out,
+                         cudaStream_t st);
+
 }  // namespace b200rl

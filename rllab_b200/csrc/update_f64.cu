@@ -251,6 +251,7 @@ int b200rl_update_f64(int mode, int loss_kind, const double* params_f64, int obs
     f.tri_partial = (mode == MODE_LOSS) ? ws : ws + (size_t)grid * P;
     f.NT = 3; f.tri_out = loss_out;
   }
+  if (peer_fused()) f.peer = peer_next();
   return launch_finalize_update(f, st);
 }
 }

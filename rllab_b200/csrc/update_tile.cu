@@ -51,38 +51,10 @@ __global__ void __launch_bounds__(T_THREADS, tile_minblocks<N, MODE>()) update_t
     for (int i = tid; i < P; i += T_THREADS) sv[i] = (float)a.xvec[i];
   __syncthreads();
 
-  // distribution constants
   TileDist D;
-  D.sum_ls_new = 0.f; D.sum_ls_old = 0.f;
-#pragma unroll
-  for (int k = 0; k < A; ++k) {
-    D.ls_new[k] = clamp_log_std(sp[N::ols + k], a.log_min_std);
-    const float sd = expf(D.ls_new[k]);
-    D.inv_std[k] = 1.0f / sd;
-    D.var_new[k] = sd * sd;
-    D.var_new2[k] = 2.0f * sd * sd + 1e-8f;
-    D.Mmu[k] = 2.0f / D.var_new2[k];
-    D.ls_old[k] = (MODE == MODE_FVP) ? D.ls_new[k] : a.old_log_std[k];
-    const float so = expf(D.ls_old[k]);
-    D.inv_std_old[k] = 1.0f / so;
-    D.var_old[k] = so * so;
-    D.sum_ls_new += D.ls_new[k];
-    D.sum_ls_old += D.ls_old[k];
-  }
-  D.half_log2pi_A = 0.5f * (float)A * 1.8378770664093453f;
-
-  // ---- Gram ownership
-  const int w1_tile = tid & 63, kh = tid >> 6;
-  const int ti = w1_tile >> 3, tj = w1_tile & 7;
-  double accW1[4][4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) accW1[r][c] = 0.0;
-  constexpr int NS = (O + 1 > A + 1) ? O + 1 : A + 1;
-  double accS[NS];   // small-output accumulators of this thread's task (see below)
-#pragma unroll
-  for (int k = 0; k < NS; ++k) accS[k] = 0.0;
+  tile_dist_init<N, MODE>(D, sp + N::ols, a);
+  TileGram<N, SM::rX, SM::rH1, SM::rH2, SM::rD1, SM::rD2, SM::rDM, LD> gram;
+  gram.init();
   double s_loss = 0.0, s_kl = 0.0, m_kl = -1.0e300;
 
   const long long ntiles = n_tiles_of(a, T_TILE);
@@ -94,117 +66,14 @@ __global__ void __launch_bounds__(T_THREADS, tile_minblocks<N, MODE>()) update_t
     // ================= phase A: per-sample forward / (tangent) / backward, staged to shared memory
     tile_phase_a<N, MODE, SM, LD>(a, sp, sv, stage, D, inrange ? s : a.B - 1, inrange, valid, tid, s_loss, s_kl, m_kl);
     __syncthreads();
-    // ================= phase B: Gram accumulation over the tile
-    {
-      float acc[4][4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-      const float* U = stage + (SM::rH1 + ti) * LD + kh * 64;
-      const float* V = stage + (SM::rD2 + tj) * LD + kh * 64;
-#pragma unroll 4
-      for (int k = 0; k < 64; k += 4) {
-        float4 u[4], v[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) u[r] = *reinterpret_cast<const float4*>(U + r * 8 * LD + k);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(V + c * 8 * LD + k);
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            acc[r][c] = fmaf(u[r].x, v[c].x, acc[r][c]);
-            acc[r][c] = fmaf(u[r].y, v[c].y, acc[r][c]);
-            acc[r][c] = fmaf(u[r].z, v[c].z, acc[r][c]);
-            acc[r][c] = fmaf(u[r].w, v[c].w, acc[r][c]);
-          }
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) accW1[r][c] += (double)acc[r][c];
-      // small outputs: warp 0 -> (dW0[:,j], db0[j]); warp 1 -> (dWout[j,:], db1[j]); warp 2 lanes < 2A -> dbout / dlog_std
-      if (tid < 32) {
-        float sa[O + 1];
-#pragma unroll
-        for (int o = 0; o <= O; ++o) sa[o] = 0.f;
-        const float* D = stage + (SM::rD1 + tid) * LD;
-#pragma unroll 4
-        for (int k = 0; k < T_TILE; k += 4) {
-          const float4 d = *reinterpret_cast<const float4*>(D + k);
-#pragma unroll
-          for (int o = 0; o < O; ++o) {
-            const float4 xv = *reinterpret_cast<const float4*>(stage + (SM::rX + o) * LD + k);
-            sa[o] = fmaf(xv.x, d.x, sa[o]); sa[o] = fmaf(xv.y, d.y, sa[o]);
-            sa[o] = fmaf(xv.z, d.z, sa[o]); sa[o] = fmaf(xv.w, d.w, sa[o]);
-          }
-          sa[O] += (d.x + d.y) + (d.z + d.w);
-        }
-#pragma unroll
-        for (int o = 0; o <= O; ++o) accS[o] += (double)sa[o];
-      } else if (tid < 64) {
-        const int j = tid - 32;
-        float sa[A + 1];
-#pragma unroll
-        for (int k = 0; k <= A; ++k) sa[k] = 0.f;
-        const float* Hh = stage + (SM::rH2 + j) * LD;
-        const float* D = stage + (SM::rD2 + j) * LD;
-#pragma unroll 4
-        for (int k = 0; k < T_TILE; k += 4) {
-          const float4 hv = *reinterpret_cast<const float4*>(Hh + k);
-          const float4 d = *reinterpret_cast<const float4*>(D + k);
-#pragma unroll
-          for (int q = 0; q < A; ++q) {
-            const float4 m = *reinterpret_cast<const float4*>(stage + (SM::rDM + q) * LD + k);
-            sa[q] = fmaf(hv.x, m.x, sa[q]); sa[q] = fmaf(hv.y, m.y, sa[q]);
-            sa[q] = fmaf(hv.z, m.z, sa[q]); sa[q] = fmaf(hv.w, m.w, sa[q]);
-          }
-          sa[A] += (d.x + d.y) + (d.z + d.w);
-        }
-#pragma unroll
-        for (int k = 0; k <= A; ++k) accS[k] += (double)sa[k];
-      } else if (tid < 64 + 2 * A) {
-        const float* D = stage + (SM::rDM + (tid - 64)) * LD;   // rows DM[0..A-1], DL[0..A-1] are contiguous
-        float s0 = 0.f;
-#pragma unroll 4
-        for (int k = 0; k < T_TILE; k += 4) {
-          const float4 d = *reinterpret_cast<const float4*>(D + k);
-          s0 += (d.x + d.y) + (d.z + d.w);
-        }
-        accS[0] += (double)s0;
-      }
-    }
+    // ================= phase B: Gram accumulation over the tile (tile_gram.cuh)
+    gram.accumulate(stage, tid);
     __syncthreads();
   }
 
   // ================= write this block's partial vector (float64)
   double* out = a.partial + (size_t)blockIdx.x * P;
-  double* scr = reinterpret_cast<double*>(stage);   // [2][64][16]
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) scr[(kh * 64 + w1_tile) * 16 + r * 4 + c] = accW1[r][c];
-  __syncthreads();
-  if (tid < 64) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        out[N::oW1 + (ti + 8 * r) * H + (tj + 8 * c)] = scr[w1_tile * 16 + r * 4 + c] + scr[(64 + w1_tile) * 16 + r * 4 + c];
-  }
-  if (tid < 32) {
-#pragma unroll
-    for (int o = 0; o < O; ++o) out[N::oW0 + o * H + tid] = accS[o];
-    out[N::ob0 + tid] = accS[O];
-  } else if (tid < 64) {
-    const int j = tid - 32;
-#pragma unroll
-    for (int k = 0; k < A; ++k) out[N::oWo + j * A + k] = accS[k];
-    out[N::ob1 + j] = accS[A];
-  } else if (tid < 64 + 2 * A) {
-    out[N::obo + (tid - 64)] = accS[0];   // obo.. then ols.. are contiguous in the flat layout
-  }
+  gram.write(out, reinterpret_cast<double*>(stage), tid);   // scratch [2][64][16] doubles in the (idle) stage region
   if constexpr (MODE == MODE_GRAD) {
     __syncthreads();
     double v[2] = {s_loss, s_kl};

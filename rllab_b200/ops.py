@@ -167,28 +167,56 @@ def lfb_solve(obs_dim, gram, reg_coeff, w_out, info_out):
     L.call("b200rl_lfb_solve", obs_dim, L.ptr(gram), float(reg_coeff), L.ptr(w_out), L.ptr(info_out), _stream())
 
 
-def loss_kl(loss_kind, params32, dims, min_std, batch, out):
-    """out[3] = (surrogate loss, mean KL, max KL) of this rank's samples, already divided by the global sample count."""
+class _Fused(object):
+    """`with _Fused(fuse):` -- the update pass launched inside reduces its outputs over the ranks of the bound peer-memory
+    communicator in its own finalize kernel (csrc/peer.cuh).  The switch is per call, not per process: a process may drive
+    a sharded job and a single-rank job side by side (bench.py's shard check does)."""
+
+    def __init__(self, fuse):
+        self.fuse = bool(fuse)
+
+    def __enter__(self):
+        if self.fuse:
+            L.call("b200rl_peer_fuse_updates", 1)
+
+    def __exit__(self, *exc):
+        if self.fuse:
+            L.call("b200rl_peer_fuse_updates", 0)
+        return False
+
+
+def peer_allreduce_mixed(t, n_sum):
+    """In place over the bound peer-memory communicator: t[:n_sum] summed, t[n_sum:] maximised over ranks (rank order)."""
+    _chk(t, F64, "t")
+    L.call("b200rl_peer_allreduce_mixed", L.ptr(t), t.numel(), int(n_sum), _stream())
+
+
+def loss_kl(loss_kind, params32, dims, min_std, batch, out, fuse=False):
+    """out[3] = (surrogate loss, mean KL, max KL) of this rank's samples, already divided by the global sample count
+    (fuse=True: of all ranks' samples)."""
     O, h1, h2, A = dims
     b = batch
     fl, scale, cnt = _mask(b)
     _chk(params32, F32, "params32"), _chk(out, F64, "out", 3)
-    L.call("b200rl_loss_kl", loss_kind, L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
-           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), fl, scale, cnt, L.ptr(out),
-           L.ptr(workspace(b.device)), _stream())
+    with _Fused(fuse):
+        L.call("b200rl_loss_kl", loss_kind, L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
+               L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), fl, scale, cnt, L.ptr(out),
+               L.ptr(workspace(b.device)), _stream())
 
 
-def grad(loss_kind, params32, dims, min_std, batch, g_out, loss_out=None, h_cache=None):
+def grad(loss_kind, params32, dims, min_std, batch, g_out, loss_out=None, h_cache=None, fuse=False):
     O, h1, h2, A = dims
     b = batch
     fl, scale, cnt = _mask(b)
     _chk(params32, F32, "params32"), _chk(g_out, F64, "g_out")
-    L.call("b200rl_grad", loss_kind, L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
-           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), fl, scale, cnt, L.ptr(g_out), L.ptr(loss_out),
-           L.ptr(h_cache), L.ptr(workspace(b.device)), _stream())
+    with _Fused(fuse):
+        L.call("b200rl_grad", loss_kind, L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
+               L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), fl, scale, cnt, L.ptr(g_out), L.ptr(loss_out),
+               L.ptr(h_cache), L.ptr(workspace(b.device)), _stream())
 
 
-def fvp(params32, dims, min_std, batch, x, reg_coeff, diag_scale, Hx_out, h_cache=None, tile_list=None, count=None):
+def fvp(params32, dims, min_std, batch, x, reg_coeff, diag_scale, Hx_out, h_cache=None, tile_list=None, count=None,
+        fuse=False):
     """tile_list (int32 device tensor) + count (float64 device scalar: valid samples in those tiles over all ranks):
     the sub-sampled product of subsample_factor < 1."""
     O, h1, h2, A = dims
@@ -197,9 +225,10 @@ def fvp(params32, dims, min_std, batch, x, reg_coeff, diag_scale, Hx_out, h_cach
     if tile_list is not None:
         scale, cnt = 1.0, L.ptr(count)
     _chk(params32, F32, "params32"), _chk(x, F64, "x"), _chk(Hx_out, F64, "Hx_out", x.numel())
-    L.call("b200rl_fvp", L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs), fl, L.ptr(x), scale,
-           cnt, float(reg_coeff), float(diag_scale), L.ptr(Hx_out), L.ptr(h_cache), L.ptr(tile_list),
-           0 if tile_list is None else int(tile_list.numel()), L.ptr(workspace(b.device)), _stream())
+    with _Fused(fuse):
+        L.call("b200rl_fvp", L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs), fl, L.ptr(x), scale,
+               cnt, float(reg_coeff), float(diag_scale), L.ptr(Hx_out), L.ptr(h_cache), L.ptr(tile_list),
+               0 if tile_list is None else int(tile_list.numel()), L.ptr(workspace(b.device)), _stream())
 
 
 def count_valid(batch, tile_list, out):
@@ -208,15 +237,16 @@ def count_valid(batch, tile_list, out):
            0 if tile_list is None else int(tile_list.numel()), L.ptr(out), L.ptr(workspace(b.device)), _stream())
 
 
-def update_f64(mode, loss_kind, params64, dims, min_std, batch, x, reg_coeff, diag_scale, vec_out, loss_out):
+def update_f64(mode, loss_kind, params64, dims, min_std, batch, x, reg_coeff, diag_scale, vec_out, loss_out, fuse=False):
     """float64 parity-mode pass: mode 0 loss/KL, 1 gradient (+loss), 2 Fisher-vector product."""
     O, h1, h2, A = dims
     b = batch
     fl, scale, cnt = _mask(b)
     _chk(params64, F64, "params64"), _chk(x, F64, "x"), _chk(vec_out, F64, "vec_out"), _chk(loss_out, F64, "loss_out", 3)
-    L.call("b200rl_update_f64", mode, loss_kind, L.ptr(params64), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
-           L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), fl, L.ptr(x), scale, cnt, float(reg_coeff),
-           float(diag_scale), L.ptr(vec_out), L.ptr(loss_out), L.ptr(workspace(b.device)), _stream())
+    with _Fused(fuse):
+        L.call("b200rl_update_f64", mode, loss_kind, L.ptr(params64), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs),
+               L.ptr(b.act), L.ptr(b.adv), L.ptr(b.mean), L.ptr(b.log_std), fl, L.ptr(x), scale, cnt, float(reg_coeff),
+               float(diag_scale), L.ptr(vec_out), L.ptr(loss_out), L.ptr(workspace(b.device)), _stream())
 
 
 def cg_init(g, x, r, p, st, p_f32=False):

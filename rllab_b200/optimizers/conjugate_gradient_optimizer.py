@@ -105,6 +105,15 @@ class ConjugateGradientOptimizer(object):
         if self._world() > 1:
             self._comm.all_reduce_mixed(t, t.numel() if n_sum is None else n_sum)
 
+    def _fuse(self):
+        """Update passes reduce over ranks inside their own finalize kernel (peer-memory transport, csrc/peer.cuh)."""
+        return self._world() > 1 and self._comm.fuse
+
+    def _after_pass(self, t, n_sum=None):
+        """Make the output of an update pass launched with fuse=self._fuse() global (no-op when it was fused)."""
+        if self._world() > 1:
+            self._comm.after_pass(t, t.numel() if n_sum is None else n_sum)
+
     def _eval(self, batch, want_grad=False):
         """surrogate loss, mean KL, max KL at the target's current parameters (one pass over the batch).
         want_grad: run the gradient pass instead, which yields the same triple for free and leaves the flat
@@ -119,21 +128,22 @@ class ConjugateGradientOptimizer(object):
         if want_grad:
             if self._f64:
                 ops.update_f64(1, self._loss_kind, pol.theta64, pol.dims, pol.min_std, batch, None, 0.0, 0.0, b["g"],
-                               b["gout"])
+                               b["gout"], fuse=self._fuse())
             else:
                 hc = batch.hcache(pol.h1, pol.h2) if self._use_hcache else None
-                ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, b["g"], b["gout"], hc)
+                ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, b["g"], b["gout"], hc,
+                         fuse=self._fuse())
                 self._hc_key = key if hc is not None else None
-            self._reduce(b["gl"], P + 2)
+            self._after_pass(b["gl"], P + 2)
             self._g_key = key
             src = b["gout"]
         else:
             if self._f64:
                 ops.update_f64(0, self._loss_kind, pol.theta64, pol.dims, pol.min_std, batch, None, 0.0, 0.0, None,
-                               b["out"])
+                               b["out"], fuse=self._fuse())
             else:
-                ops.loss_kl(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, b["out"])
-            self._reduce(b["out"], 2)
+                ops.loss_kl(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, b["out"], fuse=self._fuse())
+            self._after_pass(b["out"], 2)
             src = b["out"]
         vals = ops.LazyTriple(src)            # pinned-memory readback queued behind the pass; blocks when indexed
         self._cache = (key, vals)
@@ -175,7 +185,8 @@ class ConjugateGradientOptimizer(object):
 
             def grad_kl(sign, vec, out):
                 ops.axpy_params(theta, vec, -sign * eps, b["tmp2"], b["scratch32"])      # theta + sign * eps * x
-                ops.update_f64(1, L.LOSS_KL, b["tmp2"], pol.dims, pol.min_std, batch, None, 0.0, 0.0, out, None)
+                ops.update_f64(1, L.LOSS_KL, b["tmp2"], pol.dims, pol.min_std, batch, None, 0.0, 0.0, out, None,
+                               fuse=self._fuse())
 
             def Hx(vec, out):
                 grad_kl(+1.0, vec, out)
@@ -185,18 +196,18 @@ class ConjugateGradientOptimizer(object):
                 else:
                     grad_kl(0.0, vec, b["tmp"])
                     out.sub_(b["tmp"]).div_(eps)
-                self._reduce(out)
+                self._after_pass(out)               # both gradients were made global by their own passes when fused
                 out.add_(vec, alpha=self._reg_coeff)
             return Hx
 
         def Hx(vec, out):
             if self._f64:
                 ops.update_f64(2, self._loss_kind, pol.theta64, pol.dims, pol.min_std, batch, vec, self._reg_coeff,
-                               1.0 / world, out, None)
+                               1.0 / world, out, None, fuse=self._fuse())
             else:
                 ops.fvp(pol.theta32, pol.dims, pol.min_std, batch, vec, self._reg_coeff, 1.0 / world, out, hcache,
-                        tiles, b["cnt"] if tiles is not None else None)
-            self._reduce(out)
+                        tiles, b["cnt"] if tiles is not None else None, fuse=self._fuse())
+            self._after_pass(out)
         return Hx
 
     def optimize(self, inputs, extra_inputs=None, subsample_grouped_inputs=None):

@@ -51,16 +51,17 @@ class FirstOrderOptimizer(object):
             return self._cache[1]
         self._state(batch.device)
         active = self._comm is not None and self._comm.active
+        fuse = active and self._comm.fuse          # the pass reduces over ranks in its own finalize kernel (peer.cuh)
         if want_grad:
-            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, self._g, self._gout)
+            ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, self._g, self._gout, fuse=fuse)
             if active:
-                self._comm.all_reduce_mixed(self._gl, pol.n_params + 2)
+                self._comm.after_pass(self._gl, pol.n_params + 2)
             self._g_key = key
             src = self._gout
         else:
-            ops.loss_kl(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, self._out)
+            ops.loss_kl(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, self._out, fuse=fuse)
             if active:
-                self._comm.all_reduce_mixed(self._out, 2)
+                self._comm.after_pass(self._out, 2)
             src = self._out
         vals = ops.LazyTriple(src)            # pinned-memory readback queued behind the pass; blocks when indexed
         self._cache = (key, vals)
@@ -89,9 +90,11 @@ class FirstOrderOptimizer(object):
         last = self._eval(batch, want_grad=True)
         for epoch in range(self._max_epochs):
             if self._g_key != (pol.version, id(batch), batch.version):
-                ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, self._g, self._gout)
-                if self._comm is not None and self._comm.active:
-                    self._comm.all_reduce_mixed(self._gl, pol.n_params + 2)
+                active = self._comm is not None and self._comm.active
+                ops.grad(self._loss_kind, pol.theta32, pol.dims, pol.min_std, batch, self._g, self._gout,
+                         fuse=active and self._comm.fuse)
+                if active:
+                    self._comm.after_pass(self._gl, pol.n_params + 2)
             self._t += 1
             ops.adam_step(pol.theta64, pol.theta32, self._g, self._m, self._v, self._t, self._learning_rate, self._b1,
                           self._b2, self._eps)

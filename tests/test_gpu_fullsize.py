@@ -78,8 +78,10 @@ def test_loss_and_kl_are_exact_at_theta_old(full):
     assert abs(o[0] + float(b.adv.double().mean())) < 1e-12 and o[1] == 0.0 and o[2] == 0.0
     g = torch.zeros(full["dims"].P, dtype=torch.float64, device=full["dev"])
     out2 = torch.zeros(3, dtype=torch.float64, device=full["dev"])
+    # the gradient pass runs its forward on the tensor cores (3xTF32, update_umma32.cu): the same mean to ~1e-7, not bit
+    # for bit, so its triple is -mean(adv) / 0 to float32 rounding rather than exactly
     ops.grad(L.LOSS_TRPO, th32, (4, H, H, 1), 1e-6, b, g, out2)
-    assert abs(float(out2[0]) - o[0]) < 1e-12 and float(out2[1]) == 0.0
+    assert abs(float(out2[0]) - o[0]) < 1e-6 and abs(float(out2[1])) < 1e-10 and abs(float(out2[2])) < 1e-8
 
 
 def test_fvp_is_linear_symmetric_and_positive(full):

@@ -419,11 +419,10 @@ def _check_update_kernels(dev, env_name, hidden, N, T):
     ops.grad(L.LOSS_TRPO, th32, dd, 1e-6, b, gtmp, None, hc)
     Hx_c = torch.zeros(dims.P, dtype=torch.float64, device=dev)
     ops.fvp(th32, dd, 1e-6, b, xd, 1e-5, 1.0, Hx_c, hc)
-    if hidden == 32:
-        np.testing.assert_allclose(Hx_c.cpu().numpy(), Hx.cpu().numpy(), rtol=1e-12, atol=1e-18)
-    else:
-        # 64-wide nets with a cache run the dense chain on the tensor cores (update_umma.cu, three-pass TF32 split,
-        # float32 accumulation in TMEM): float32-grade agreement with the FFMA kernel, not bit equality
+    # with a cache the dense chain runs on the tensor cores (update_umma32.cu / update_umma.cu: three-pass TF32 split,
+    # float32 accumulation in TMEM): float32-grade agreement with the FFMA kernel, not bit equality -- and the same
+    # agreement with the float64 oracle as the FFMA kernel
+    if True:
         np.testing.assert_allclose(Hx_c.cpu().numpy(), Hx.cpu().numpy(), rtol=0, atol=5e-6 * np.abs(Hx.cpu().numpy()).max())
         ref_c = P.fvp(theta, batch, x.astype(np.float32).astype(np.float64), dims, 0.0) + 1e-5 * x
         np.testing.assert_allclose(Hx_c.cpu().numpy(), ref_c, rtol=2e-4, atol=2e-6 * np.abs(ref_c).max())
