@@ -290,7 +290,11 @@ def main():
         rel = max_over_ranks(rel)[0]
         shard_check = dict(workload="cartpole VPG, %d lanes x 50 steps, 3 iterations" % (1024 * world),
                            max_rel_diff_vs_single_process=rel)
-        assert rel < 1e-9, "sharded run differs from the single-process run: %g" % rel
+        # rollout, GAE scan, loss/KL, gradient: per-tile float32 partials over the same sample groups (shards are whole
+        # tiles), float64 above -> identical up to float64 summation order.  The baseline normal equations accumulate
+        # float32 inside one thread's ~170 samples, and that grouping depends on the shard size: 1e-7 relative in the
+        # baseline weights, ~1e-9 in theta after three Adam steps.
+        assert rel < 1e-7, "sharded run differs from the single-process run: %g" % rel
 
     # ---- per-kernel timing of the same iteration (CUDA events around each library call), for the rooflines
     env_name, algo_name, lanes, T, hidden, alg_bytes = WORKLOADS[args.workload]

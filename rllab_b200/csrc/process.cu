@@ -39,158 +39,166 @@ __device__ __forceinline__ double lfb_predict(const float* __restrict__ obs, siz
   return acc;
 }
 
-// GAE / returns reverse scan, parallel over lanes AND over time (round 2; the one-thread-per-lane walk of round 1 kept
-// only ~14 warps per SM busy at 65 536 lanes and sat at 26 % of the measured HBM bandwidth).
+// process_samples = two streaming kernels (round 2, second design; the block-cooperative time-parallel scan of the first
+// round-2 design spent its time in barriers between its load / scan / carry phases: 0.54 ms on cfg2, 13 % of HBM):
 //
-// A block owns 32 lanes (one warp-width, so every row access is one coalesced 128 B transaction) and walks T backwards
-// in WINDOWS of PS_WARPS x PS_L steps: warp c of the block owns the c-th chunk of PS_L consecutive steps of the window
-// (warp 0 = the latest steps).  The recurrences  x_t = c_t + m_t x_{t+1}  (m_t = factor, or 0 at the last sample of a
-// path) are linear, so each window is resolved with a two-pass chunked scan:
-//   P1  every thread loads its PS_L steps (all loads independent: PS_L x (O+3) in flight per thread), evaluates the
-//       baseline b_t (float64) and publishes the b of its earliest step (the delta of the chunk before it needs it),
-//   P2  local scan with zero carry-in -> values at the chunk's earliest step + "no path end inside the chunk",
-//   P3  every thread folds the aggregates of the later chunks of its lane (<= PS_WARPS-1 three-term updates) into its
-//       true carry-in,
-//   P4  second scan from the registers with the true carry: writes adv / ret, accumulates the statistics.
-// Inputs are read once and outputs written once: HBM traffic = the algorithmic 4*O+19 B per sample.
-// Recurrences and statistics in float64, as the reference runs them (sampler/base.py:57-66, special.py:107-111).
+//   lfb_predict_kernel   elementwise over the flattened (t, n) sample index, four samples per thread with 128-bit loads:
+//                        b = features(obs, tstep) . w in float64, stored as float32 `base`.  4*O + 2 B read, 4 B written per
+//                        sample, no dependence between samples -> a pure HBM stream.
+//   gae_scan_kernel      one thread per lane walks T backwards (the recurrences x_t = c_t + m_t x_{t+1} are sequential in
+//                        t) in chunks of SC_CH steps, register double-buffered: the 4 x SC_CH loads of the next chunk
+//                        (rew, base, flags, tstep -- all independent of the recurrence) are in flight while the current
+//                        chunk is scanned, i.e. ~350 B per thread outstanding at any time.  11 B read + 8 B written per
+//                        sample; float64 recurrences and statistics, as the reference runs them (sampler/base.py:57-66,
+//                        special.py:107-111).  The deltas use the float32-rounded baseline (6e-8 relative).
 //
 // drop_cut != 0: a path that carries FLAG_CUT on its last sample (cut by the end of the lane buffer) is dropped, the
 // way the reference's samplers only ever return whole paths (batch_polopt.py:30-34 with whole_paths=True;
 // vectorized_sampler.py drops unfinished running_paths): its samples get FLAG_MASKED, adv = 0, and are excluded from
 // every statistic (count, path counts, returns); downstream kernels skip masked samples.
-constexpr int PS_L = 8, PS_WARPS = 8, PS_THREADS2 = 32 * PS_WARPS, PS_WIN = PS_L * PS_WARPS;
+constexpr int PRED_THREADS = 256;
 
 template <int OT>
-__global__ void __launch_bounds__(PS_THREADS2, 2)
-    process_samples_kernel(int O, int N, int T, const float* __restrict__ obs, const float* __restrict__ rew,
-                           unsigned char* __restrict__ flags, const unsigned short* __restrict__ tstep,
-                           const double* __restrict__ w, double discount, double gl, int drop_cut,
-                           float* __restrict__ adv, float* __restrict__ ret, float* __restrict__ base,
-                           double* __restrict__ partial_sum, double* __restrict__ partial_max) {
-  __shared__ double sw[2 * OMAX + 4];
-  __shared__ double scratch[B200RL_PS_NSUM * 32];
-  __shared__ double s_bfirst[PS_WARPS][32];
-  __shared__ double s_agg[PS_WARPS][3][32];
-  __shared__ unsigned char s_st[PS_WARPS][32];     // bit0: no path end inside the chunk, bit1: local "dropped" state
-  __shared__ double s_carry[4][32];                // window carry: adv, ret, undiscounted return, b of the next step
-  __shared__ unsigned char s_mcarry[32];
-  const bool have_w = (w != nullptr);
-  if (have_w)
-    for (int i = threadIdx.x; i < 2 * O + 4; i += blockDim.x) sw[i] = w[i];
-  const int ln = threadIdx.x & 31, c = threadIdx.x >> 5;
-  if (c == 0) {
-    s_carry[0][ln] = 0.0; s_carry[1][ln] = 0.0; s_carry[2][ln] = 0.0; s_carry[3][ln] = 0.0;
-    s_mcarry[ln] = 0;
+__device__ __forceinline__ double lfb_dot(const float (&ov)[OT > 0 ? OT : 1], unsigned short ts, const double* __restrict__ w) {
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < OT; ++k) {
+    const double o = (double)fminf(fmaxf(ov[k], -10.0f), 10.0f);
+    acc += o * w[k] + (o * o) * w[OT + k];
   }
+  const double al = (double)ts / 100.0;
+  acc += al * w[2 * OT] + (al * al) * w[2 * OT + 1] + (al * al * al) * w[2 * OT + 2] + w[2 * OT + 3];
+  return acc;
+}
+
+template <int OT>
+__global__ void __launch_bounds__(PRED_THREADS) lfb_predict_kernel(int O_rt, long long B, const float* __restrict__ obs,
+                                                                   const unsigned short* __restrict__ tstep,
+                                                                   const double* __restrict__ w,
+                                                                   float* __restrict__ base) {
+  __shared__ double sw[2 * OMAX + 4];
+  const int O = OT > 0 ? OT : O_rt;
+  for (int i = threadIdx.x; i < 2 * O + 4; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
-  const int n = blockIdx.x * 32 + ln;
-  const bool lane_ok = n < N;
-  const size_t plane = (size_t)T * N;
+  const long long stride = (long long)gridDim.x * blockDim.x, gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long done = 0;
+  if constexpr (OT > 0) {
+    if ((B & 3) == 0) {            // every obs plane is 16 B aligned: 128-bit loads, 4 samples per thread
+      const long long nvec = B >> 2;
+      for (long long v = gt; v < nvec; v += stride) {
+        float4 o4[OT];
+#pragma unroll
+        for (int k = 0; k < OT; ++k) o4[k] = reinterpret_cast<const float4*>(obs + (size_t)k * B)[v];
+        const ushort4 ts = reinterpret_cast<const ushort4*>(tstep)[v];
+        float ov[4][OT];
+#pragma unroll
+        for (int k = 0; k < OT; ++k) { ov[0][k] = o4[k].x; ov[1][k] = o4[k].y; ov[2][k] = o4[k].z; ov[3][k] = o4[k].w; }
+        float4 out;
+        out.x = (float)lfb_dot<OT>(ov[0], ts.x, sw);
+        out.y = (float)lfb_dot<OT>(ov[1], ts.y, sw);
+        out.z = (float)lfb_dot<OT>(ov[2], ts.z, sw);
+        out.w = (float)lfb_dot<OT>(ov[3], ts.w, sw);
+        reinterpret_cast<float4*>(base)[v] = out;
+      }
+      done = B;
+    }
+  }
+  for (long long i = done + gt; i < B; i += stride) base[i] = (float)lfb_predict<OT>(obs, (size_t)B, (size_t)i, O, tstep[i], sw);
+}
+
+// 14 warps of 32 lanes per SM hold cfg2's 65 536 lanes in ONE wave (148 x 14 x 32 = 66 304); 8-step chunks keep the two
+// register buffers + 20 float64 statistics under the 146 registers that allows
+constexpr int SC_CH = 8, SC_THREADS = 32, SC_BLOCKS_PER_SM = 14;
+
+struct ScanChunk {     // one chunk of SC_CH steps of one lane, in registers
+  float rw[SC_CH], bs[SC_CH];
+  unsigned int fl[SC_CH];          // flags | (tstep == 0) << 8
+};
+
+__device__ __forceinline__ void scan_load(ScanChunk& c, int t_hi, int N, int n, const float* __restrict__ rew,
+                                          const float* __restrict__ base, const unsigned char* __restrict__ flags,
+                                          const unsigned short* __restrict__ tstep) {
+#pragma unroll
+  for (int u = 0; u < SC_CH; ++u) {
+    const int t = t_hi - u;
+    if (t >= 0) {
+      const size_t idx = (size_t)t * N + n;
+      c.rw[u] = rew[idx];
+      c.bs[u] = base[idx];
+      c.fl[u] = (unsigned int)flags[idx] | (tstep[idx] == 0 ? 0x100u : 0u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM)
+    gae_scan_kernel(int N, int T, const float* __restrict__ rew, const float* __restrict__ base,
+                    unsigned char* __restrict__ flags, const unsigned short* __restrict__ tstep, double discount,
+                    double gl, int drop_cut, float* __restrict__ adv, float* __restrict__ ret,
+                    double* __restrict__ partial_sum, double* __restrict__ partial_max) {
+  __shared__ double scratch[B200RL_PS_NSUM * 32];
+  const int n_raw = blockIdx.x * SC_THREADS + threadIdx.x;
+  const bool lane_ok = n_raw < N;
+  const int n = lane_ok ? n_raw : N - 1;          // out-of-range threads shadow the last lane (no stores, no statistics)
   double s[B200RL_PS_NSUM];
   double m[B200RL_PS_NMAX];
 #pragma unroll
   for (int i = 0; i < B200RL_PS_NSUM; ++i) s[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < B200RL_PS_NMAX; ++i) m[i] = -1.0e300;
-  double gl8 = gl * gl, d8 = discount * discount;     // factor ^ PS_L
-  gl8 *= gl8; gl8 *= gl8; d8 *= d8; d8 *= d8;
-  static_assert(PS_L == 8, "the factor powers above assume 8 steps per chunk");
+  double a_n = 0.0, r_n = 0.0, u_n = 0.0, b_n = 0.0;
+  bool dropped = false;
 
-  for (int win_hi = T; win_hi > 0; win_hi -= PS_WIN) {
-    const int t_hi = win_hi - 1 - c * PS_L;            // latest step of this thread's chunk
-    // ---------------- P1: loads + baseline
-    float rw[PS_L];
-    double bs[PS_L];
-    unsigned int endm = 0, startm = 0, cutm = 0;
+  auto scan = [&](const ScanChunk& c, int t_hi) {
 #pragma unroll
-    for (int u = 0; u < PS_L; ++u) {
+    for (int u = 0; u < SC_CH; ++u) {
       const int t = t_hi - u;
-      const bool act = lane_ok && t >= 0;
-      const size_t idx = (size_t)(act ? t : 0) * N + (lane_ok ? n : 0);
-      const unsigned char f = act ? flags[idx] : (unsigned char)0;
-      const unsigned short ts = act ? tstep[idx] : (unsigned short)1;
-      rw[u] = act ? rew[idx] : 0.f;
-      endm |= (unsigned)((f & B200RL_FLAG_END) ? 1 : 0) << u;
-      cutm |= (unsigned)((f & B200RL_FLAG_CUT) ? 1 : 0) << u;
-      startm |= (unsigned)(ts == 0 ? 1 : 0) << u;
-      bs[u] = (have_w && act) ? lfb_predict<OT>(obs, plane, idx, O, ts, sw) : 0.0;
-      if (act) base[idx] = (float)bs[u];
-    }
-    if (!drop_cut) cutm = 0;
-    s_bfirst[c][ln] = bs[PS_L - 1];
-    __syncthreads();
-    // ---------------- P2: local scan (zero carry-in)
-    const double b_in = (c == 0) ? s_carry[3][ln] : s_bfirst[c - 1][ln];
-    {
-      double a_n = 0.0, r_n = 0.0, u_n = 0.0, b_n = b_in;
-      bool alive = true, dropped = false;
-#pragma unroll
-      for (int u = 0; u < PS_L; ++u) {
-        if ((endm >> u) & 1u) { a_n = 0.0; r_n = 0.0; u_n = 0.0; b_n = 0.0; alive = false; dropped = (cutm >> u) & 1u; }
-        const double r = (double)rw[u];
-        a_n = (r + discount * b_n - bs[u]) + gl * a_n;
-        r_n = r + discount * r_n;
-        u_n = r + u_n;
-        b_n = bs[u];
+      if (t < 0) continue;
+      const size_t idx = (size_t)t * N + n;
+      const unsigned int f = c.fl[u];
+      if (f & B200RL_FLAG_END) {
+        a_n = 0.0; r_n = 0.0; u_n = 0.0; b_n = 0.0;
+        dropped = drop_cut && (f & B200RL_FLAG_CUT);
       }
-      s_agg[c][0][ln] = a_n; s_agg[c][1][ln] = r_n; s_agg[c][2][ln] = u_n;
-      s_st[c][ln] = (unsigned char)((alive ? 1 : 0) | (dropped ? 2 : 0));
-    }
-    __syncthreads();
-    // ---------------- P3: true carry-in of this chunk
-    double a_n = s_carry[0][ln], r_n = s_carry[1][ln], u_n = s_carry[2][ln];
-    bool dropped = s_mcarry[ln] != 0;
-    for (int cc = 0; cc < c; ++cc) {
-      const unsigned char st = s_st[cc][ln];
-      const bool alive = st & 1;
-      a_n = s_agg[cc][0][ln] + (alive ? gl8 * a_n : 0.0);
-      r_n = s_agg[cc][1][ln] + (alive ? d8 * r_n : 0.0);
-      u_n = s_agg[cc][2][ln] + (alive ? u_n : 0.0);
-      dropped = alive ? dropped : ((st & 2) != 0);
-    }
-    // ---------------- P4: second scan with the true carry, outputs + statistics
-    {
-      double b_n = b_in;
-#pragma unroll
-      for (int u = 0; u < PS_L; ++u) {
-        const int t = t_hi - u;
-        if (!(lane_ok && t >= 0)) continue;
-        const size_t idx = (size_t)t * N + n;
-        if ((endm >> u) & 1u) { a_n = 0.0; r_n = 0.0; u_n = 0.0; b_n = 0.0; dropped = (cutm >> u) & 1u; }
-        const double r = (double)rw[u], b = bs[u];
-        a_n = (r + discount * b_n - b) + gl * a_n;          // base.py:59-61, discount_cumsum(deltas, discount*lambda)
-        r_n = r + discount * r_n;                            // discount_cumsum(rewards, discount)
-        u_n = r + u_n;
-        b_n = b;
-        ret[idx] = (float)r_n;
-        if (dropped) {
-          adv[idx] = 0.f;
-          flags[idx] = (unsigned char)(((endm >> u) & 1u ? B200RL_FLAG_END : 0) | ((cutm >> u) & 1u ? B200RL_FLAG_CUT : 0) |
-                                       B200RL_FLAG_MASKED | (flags[idx] & B200RL_FLAG_DONE));
-          continue;
-        }
-        adv[idx] = (float)a_n;
-        // statistics use the float64 values (as the reference does)
-        s[0] += a_n; s[1] += a_n * a_n; s[2] += 1.0;
-        s[7] += r_n; s[8] += r_n * r_n; s[9] += b; s[10] += b * b;
-        const double res = r_n - b;
-        s[11] += res; s[12] += res * res;
-        m[2] = fmax(m[2], -a_n); m[3] = fmax(m[3], a_n);
-        if ((startm >> u) & 1u) {  // first sample of a path
-          s[3] += 1.0; s[4] += r_n; s[5] += u_n; s[6] += u_n * u_n;
-          m[0] = fmax(m[0], u_n); m[1] = fmax(m[1], -u_n);
-        }
+      const double r = (double)c.rw[u], b = (double)c.bs[u];
+      a_n = (r + discount * b_n - b) + gl * a_n;          // base.py:59-61, discount_cumsum(deltas, discount*lambda)
+      r_n = r + discount * r_n;                            // discount_cumsum(rewards, discount)
+      u_n = r + u_n;
+      b_n = b;
+      if (!lane_ok) continue;
+      ret[idx] = (float)r_n;
+      if (dropped) {
+        adv[idx] = 0.f;
+        flags[idx] = (unsigned char)((f & 0xFFu) | B200RL_FLAG_MASKED);
+        continue;
+      }
+      adv[idx] = (float)a_n;
+      // statistics use the float64 values (as the reference does)
+      s[0] += a_n; s[1] += a_n * a_n; s[2] += 1.0;
+      s[7] += r_n; s[8] += r_n * r_n; s[9] += b; s[10] += b * b;
+      const double res = r_n - b;
+      s[11] += res; s[12] += res * res;
+      m[2] = fmax(m[2], -a_n); m[3] = fmax(m[3], a_n);
+      if (f & 0x100u) {  // first sample of a path
+        s[3] += 1.0; s[4] += r_n; s[5] += u_n; s[6] += u_n * u_n;
+        m[0] = fmax(m[0], u_n); m[1] = fmax(m[1], -u_n);
       }
     }
-    // window carry-out: the chunk that holds the earliest steps of the window (read again only after the next
-    // window's first barrier)
-    if (c == PS_WARPS - 1) {
-      s_carry[0][ln] = a_n; s_carry[1][ln] = r_n; s_carry[2][ln] = u_n; s_carry[3][ln] = bs[PS_L - 1];
-      s_mcarry[ln] = dropped ? 1 : 0;
-    }
+  };
+
+  // the compiler barriers pin the loads of the NEXT chunk ahead of the scan of the current one (ptxas otherwise sinks
+  // them to their first use, which serialises a DRAM round trip per chunk: 0.29 ms instead of 0.1 on cfg2)
+  ScanChunk ca, cb;
+  scan_load(ca, T - 1, N, n, rew, base, flags, tstep);
+  for (int t_hi = T - 1; t_hi >= 0; t_hi -= 2 * SC_CH) {
+    scan_load(cb, t_hi - SC_CH, N, n, rew, base, flags, tstep);
+    asm volatile("" ::: "memory");
+    scan(ca, t_hi);
+    asm volatile("" ::: "memory");
+    scan_load(ca, t_hi - 2 * SC_CH, N, n, rew, base, flags, tstep);
+    asm volatile("" ::: "memory");
+    scan(cb, t_hi - SC_CH);
+    asm volatile("" ::: "memory");
   }
-  __syncthreads();
   block_reduce_store<B200RL_PS_NSUM, false>(s, scratch, partial_sum + (size_t)blockIdx.x * B200RL_PS_NSUM);
   block_reduce_store<B200RL_PS_NMAX, true>(m, scratch, partial_max + (size_t)blockIdx.x * B200RL_PS_NMAX);
 }
@@ -375,26 +383,34 @@ int b200rl_process_samples(int obs_dim, int N, int T, const float* obs, const fl
   B200RL_REQUIRE(obs && rew && flags && tstep && adv && ret && base && sums_out && maxs_out && ws,
                  "process_samples: null buffer");
   B200RL_REQUIRE(N > 0 && T > 0 && obs_dim > 0 && obs_dim <= OMAX, "process_samples: bad sizes");
-  const int grid = (N + 31) / 32;          // one block per 32 lanes (PS_WARPS warps walk T in windows)
-  B200RL_REQUIRE(grid <= 262144, "process_samples: too many lanes for one call (N <= 8M)");
+  const int grid = (N + SC_THREADS - 1) / SC_THREADS;          // scan: one thread per lane
   cudaStream_t st = (cudaStream_t)stream;
   double* psum = ws;
   double* pmax = ws + (size_t)grid * B200RL_PS_NSUM;
   B200RL_REQUIRE((long long)grid * (B200RL_PS_NSUM + B200RL_PS_NMAX) <= b200rl_ws_doubles(), "workspace too small");
-#define B200RL_PS_LAUNCH(OT)                                                                                     \
-  process_samples_kernel<OT><<<grid, PS_THREADS2, 0, st>>>(obs_dim, N, T, obs, rew, flags, tstep, w, discount,        \
-                                                           discount * gae_lambda, drop_cut_paths, adv, ret, base, psum, \
-                                                           pmax)
-  switch (obs_dim) {                 // the obs dims of the compiled envs get an unrolled baseline predictor
-    case 2: B200RL_PS_LAUNCH(2); break;
-    case 3: B200RL_PS_LAUNCH(3); break;
-    case 4: B200RL_PS_LAUNCH(4); break;
-    case 13: B200RL_PS_LAUNCH(13); break;
-    case 20: B200RL_PS_LAUNCH(20); break;
-    default: B200RL_PS_LAUNCH(0); break;
+  const long long B = (long long)N * T;
+  if (w == nullptr) {                      // first iteration: the reference's baseline predicts zeros
+    B200RL_CUDA_CHECK(cudaMemsetAsync(base, 0, (size_t)B * sizeof(float), st));
+  } else {
+    long long pg = (B / 4 + PRED_THREADS - 1) / PRED_THREADS;
+    const long long cap = (long long)num_sms() * 16;
+    if (pg > cap) pg = cap;
+    if (pg < 1) pg = 1;
+#define B200RL_PRED_LAUNCH(OT) lfb_predict_kernel<OT><<<(unsigned)pg, PRED_THREADS, 0, st>>>(obs_dim, B, obs, tstep, w, base)
+    switch (obs_dim) {                 // the obs dims of the compiled envs get an unrolled, vectorised predictor
+      case 2: B200RL_PRED_LAUNCH(2); break;
+      case 3: B200RL_PRED_LAUNCH(3); break;
+      case 4: B200RL_PRED_LAUNCH(4); break;
+      case 13: B200RL_PRED_LAUNCH(13); break;
+      case 20: B200RL_PRED_LAUNCH(20); break;
+      default: B200RL_PRED_LAUNCH(0); break;
+    }
+#undef B200RL_PRED_LAUNCH
+    B200RL_LAUNCH_CHECK("lfb_predict_kernel");
   }
-#undef B200RL_PS_LAUNCH
-  B200RL_LAUNCH_CHECK("process_samples_kernel");
+  gae_scan_kernel<<<grid, SC_THREADS, 0, st>>>(N, T, rew, base, flags, tstep, discount, discount * gae_lambda,
+                                               drop_cut_paths, adv, ret, psum, pmax);
+  B200RL_LAUNCH_CHECK("gae_scan_kernel");
   int rc = launch_finalize_sum(psum, grid, B200RL_PS_NSUM, sums_out, 1.0, st);
   if (rc) return rc;
   return launch_finalize_max(pmax, grid, B200RL_PS_NMAX, maxs_out, st);

@@ -39,14 +39,24 @@ __device__ __forceinline__ void tile_dist_init(TileDist& D, const float* log_std
   D.half_log2pi_A = 0.5f * (float)A * 1.8378770664093453f;
 }
 
-// RX..RDL: first stage row of X, H1, H2, D1, D2, DM (DL rows follow DM); LD: row pitch in floats (tile + 4)
-template <class N, int RX, int RH1, int RH2, int RD1, int RD2, int RDM, int LD>
+// RX..RDM: first stage row of X, H1, H2, D1, D2, DM (DL rows follow DM); LD: row pitch in floats (tile + 4).
+// The accumulation is split in two parts so that a caller whose D1 rows only exist later (update_umma32.cu: D1 needs one
+// more tensor-core GEMM) can run part A behind that GEMM, and may alias the D1 rows with the H2 rows (dead after part A):
+//   part A  dW1 = H1^T D2 (all 128 threads: 4x4 register tiles x two K-halves), dWout[:, k] / db1 (warp k / warp 3),
+//           dbout / dlog_std row sums (threads < 2A)                                   -- reads H1, H2, D2, DM, DL
+//   part B  dW0[o, :] for o = warp, warp + 4, ... and db0 (warp 3)                     -- reads X, D1
+// Every small output is spread over the four warps: with one warp per output group (the first layout) warp 0 carried
+// dW1 + all of dW0 -- 2.7x the work of the others for obs_dim 13 -- and set the length of the phase.
+// PACKED: dW1 with packed FFMA2 (two samples per instruction, even / odd partial sums).
+template <class N, int RX, int RH1, int RH2, int RD1, int RD2, int RDM, int LD, bool PACKED = false>
 struct TileGram {
   static constexpr int O = N::O, H = 32, A = N::A, TILE = 128;
-  static constexpr int NS = (O + 1 > A + 1) ? O + 1 : A + 1;
-  static_assert(N::H1 == 32 && N::H2 == 32, "32-wide layers");
+  static constexpr int OQ = (O + 3) / 4;          // obs rows per warp in part B
+  static_assert(N::H1 == 32 && N::H2 == 32 && A <= 3, "32-wide layers, act_dim <= 3");
   double accW1[4][4];
-  double accS[NS];   // small-output accumulators of this thread's task
+  double accB[OQ + 1];   // part B: dW0[warp + 4 i][lane], i < OQ; [OQ]: db0[lane] (warp 3)
+  double accA;           // part A: dWout[lane][warp] (warp < A) | db1[lane] (warp 3)
+  double accT;           // part A: dbout[tid] / dlog_std[tid - A] row sums (tid < 2A)
 
   __device__ __forceinline__ void init() {
 #pragma unroll
@@ -54,90 +64,121 @@ struct TileGram {
 #pragma unroll
       for (int c = 0; c < 4; ++c) accW1[r][c] = 0.0;
 #pragma unroll
-    for (int k = 0; k < NS; ++k) accS[k] = 0.0;
+    for (int k = 0; k <= OQ; ++k) accB[k] = 0.0;
+    accA = 0.0;
+    accT = 0.0;
   }
 
-  __device__ __forceinline__ void accumulate(const float* stage, int tid) {
+  __device__ __forceinline__ void accumulate_a(const float* stage, int tid) {
     const int w1_tile = tid & 63, kh = tid >> 6;
     const int ti = w1_tile >> 3, tj = w1_tile & 7;
-    float acc[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
     const float* U = stage + (RH1 + ti) * LD + kh * 64;
     const float* V = stage + (RD2 + tj) * LD + kh * 64;
-#pragma unroll 4
-    for (int k = 0; k < 64; k += 4) {
-      float4 u[4], v[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) u[r] = *reinterpret_cast<const float4*>(U + r * 8 * LD + k);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(V + c * 8 * LD + k);
+    if constexpr (PACKED) {
+      float2 acc[4][4];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          acc[r][c] = fmaf(u[r].x, v[c].x, acc[r][c]);
-          acc[r][c] = fmaf(u[r].y, v[c].y, acc[r][c]);
-          acc[r][c] = fmaf(u[r].z, v[c].z, acc[r][c]);
-          acc[r][c] = fmaf(u[r].w, v[c].w, acc[r][c]);
-        }
-    }
+        for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
+#pragma unroll 2
+      for (int k = 0; k < 64; k += 4) {
+        float4 u[4], v[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r) u[r] = *reinterpret_cast<const float4*>(U + r * 8 * LD + k);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) accW1[r][c] += (double)acc[r][c];
-    // small outputs: warp 0 -> (dW0[:,j], db0[j]); warp 1 -> (dWout[j,:], db1[j]); warp 2 lanes < 2A -> dbout / dlog_std
-    if (tid < 32) {
-      float sa[O + 1];
-#pragma unroll
-      for (int o = 0; o <= O; ++o) sa[o] = 0.f;
-      const float* D = stage + (RD1 + tid) * LD;
-#pragma unroll 4
-      for (int k = 0; k < TILE; k += 4) {
-        const float4 d = *reinterpret_cast<const float4*>(D + k);
-#pragma unroll
-        for (int o = 0; o < O; ++o) {
-          const float4 xv = *reinterpret_cast<const float4*>(stage + (RX + o) * LD + k);
-          sa[o] = fmaf(xv.x, d.x, sa[o]); sa[o] = fmaf(xv.y, d.y, sa[o]);
-          sa[o] = fmaf(xv.z, d.z, sa[o]); sa[o] = fmaf(xv.w, d.w, sa[o]);
-        }
-        sa[O] += (d.x + d.y) + (d.z + d.w);
+        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(V + c * 8 * LD + k);
+        gram_4x4(u, v, acc);
       }
 #pragma unroll
-      for (int o = 0; o <= O; ++o) accS[o] += (double)sa[o];
-    } else if (tid < 64) {
-      const int j = tid - 32;
-      float sa[A + 1];
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int k = 0; k <= A; ++k) sa[k] = 0.f;
-      const float* Hh = stage + (RH2 + j) * LD;
-      const float* D = stage + (RD2 + j) * LD;
+        for (int c = 0; c < 4; ++c) accW1[r][c] += (double)(acc[r][c].x + acc[r][c].y);
+    } else {
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < 64; k += 4) {
+        float4 u[4], v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) u[r] = *reinterpret_cast<const float4*>(U + r * 8 * LD + k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(V + c * 8 * LD + k);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            acc[r][c] = fmaf(u[r].x, v[c].x, acc[r][c]);
+            acc[r][c] = fmaf(u[r].y, v[c].y, acc[r][c]);
+            acc[r][c] = fmaf(u[r].z, v[c].z, acc[r][c]);
+            acc[r][c] = fmaf(u[r].w, v[c].w, acc[r][c]);
+          }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) accW1[r][c] += (double)acc[r][c];
+    }
+    // small outputs of part A: warp k < A -> dWout[lane][k] = H2[lane] . DM[k]; warp 3 -> db1[lane] = sum D2[lane]
+    const int lane = tid & 31, wq = tid >> 5;
+    if (wq < A) {
+      const float* Hh = stage + (RH2 + lane) * LD;
+      const float* M = stage + (RDM + wq) * LD;
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll 4
       for (int k = 0; k < TILE; k += 4) {
         const float4 hv = *reinterpret_cast<const float4*>(Hh + k);
-        const float4 d = *reinterpret_cast<const float4*>(D + k);
-#pragma unroll
-        for (int q = 0; q < A; ++q) {
-          const float4 m = *reinterpret_cast<const float4*>(stage + (RDM + q) * LD + k);
-          sa[q] = fmaf(hv.x, m.x, sa[q]); sa[q] = fmaf(hv.y, m.y, sa[q]);
-          sa[q] = fmaf(hv.z, m.z, sa[q]); sa[q] = fmaf(hv.w, m.w, sa[q]);
-        }
-        sa[A] += (d.x + d.y) + (d.z + d.w);
+        const float4 m = *reinterpret_cast<const float4*>(M + k);
+        s0 = fmaf(hv.x, m.x, s0); s1 = fmaf(hv.y, m.y, s1);
+        s0 = fmaf(hv.z, m.z, s0); s1 = fmaf(hv.w, m.w, s1);
       }
-#pragma unroll
-      for (int k = 0; k <= A; ++k) accS[k] += (double)sa[k];
-    } else if (tid < 64 + 2 * A) {
-      const float* D = stage + (RDM + (tid - 64)) * LD;   // rows DM[0..A-1], DL[0..A-1] are contiguous
+      accA += (double)(s0 + s1);
+    } else if (wq == 3) {
+      const float* Dr = stage + (RD2 + lane) * LD;
       float s0 = 0.f;
 #pragma unroll 4
       for (int k = 0; k < TILE; k += 4) {
-        const float4 d = *reinterpret_cast<const float4*>(D + k);
+        const float4 d = *reinterpret_cast<const float4*>(Dr + k);
         s0 += (d.x + d.y) + (d.z + d.w);
       }
-      accS[0] += (double)s0;
+      accA += (double)s0;
     }
+    if (tid < 2 * A) {
+      const float* Dr = stage + (RDM + tid) * LD;   // rows DM[0..A-1], DL[0..A-1] are contiguous
+      float s0 = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < TILE; k += 4) {
+        const float4 d = *reinterpret_cast<const float4*>(Dr + k);
+        s0 += (d.x + d.y) + (d.z + d.w);
+      }
+      accT += (double)s0;
+    }
+  }
+
+  __device__ __forceinline__ void accumulate_b(const float* stage, int tid) {
+    const int lane = tid & 31, wq = tid >> 5;
+    const float* Dr = stage + (RD1 + lane) * LD;
+    float sa[OQ + 1];
+#pragma unroll
+    for (int i = 0; i <= OQ; ++i) sa[i] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < TILE; k += 4) {
+      const float4 d = *reinterpret_cast<const float4*>(Dr + k);
+#pragma unroll
+      for (int i = 0; i < OQ; ++i) {
+        const int o = wq + 4 * i;
+        if (o < O) {
+          const float4 xv = *reinterpret_cast<const float4*>(stage + (RX + o) * LD + k);
+          sa[i] = fmaf(xv.x, d.x, sa[i]); sa[i] = fmaf(xv.y, d.y, sa[i]);
+          sa[i] = fmaf(xv.z, d.z, sa[i]); sa[i] = fmaf(xv.w, d.w, sa[i]);
+        }
+      }
+      if (wq == 3) sa[OQ] += (d.x + d.y) + (d.z + d.w);
+    }
+#pragma unroll
+    for (int i = 0; i <= OQ; ++i) accB[i] += (double)sa[i];
   }
 
   // out: this block's partial vector [P]; scr: >= 2 * 64 * 16 doubles of shared memory no thread still reads
@@ -156,18 +197,19 @@ struct TileGram {
         for (int c = 0; c < 4; ++c)
           out[N::oW1 + (ti + 8 * r) * H + (tj + 8 * c)] = scr[w1_tile * 16 + r * 4 + c] + scr[(64 + w1_tile) * 16 + r * 4 + c];
     }
-    if (tid < 32) {
+    const int lane = tid & 31, wq = tid >> 5;
 #pragma unroll
-      for (int o = 0; o < O; ++o) out[N::oW0 + o * H + tid] = accS[o];
-      out[N::ob0 + tid] = accS[O];
-    } else if (tid < 64) {
-      const int j = tid - 32;
-#pragma unroll
-      for (int k = 0; k < A; ++k) out[N::oWo + j * A + k] = accS[k];
-      out[N::ob1 + j] = accS[A];
-    } else if (tid < 64 + 2 * A) {
-      out[N::obo + (tid - 64)] = accS[0];   // obo.. then ols.. are contiguous in the flat layout
+    for (int i = 0; i < OQ; ++i) {
+      const int o = wq + 4 * i;
+      if (o < O) out[N::oW0 + o * H + lane] = accB[i];
     }
+    if (wq == 3) {
+      out[N::ob0 + lane] = accB[OQ];
+      out[N::ob1 + lane] = accA;
+    } else if (wq < A) {
+      out[N::oWo + lane * A + wq] = accA;
+    }
+    if (tid < 2 * A) out[N::obo + tid] = accT;   // obo.. then ols.. are contiguous in the flat layout
   }
 };
 

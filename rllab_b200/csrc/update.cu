@@ -157,7 +157,11 @@ int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int
 #else
   int rc = (h1 == 32) ? update_umma32_launch(MODE_GRAD, obs_dim, act_dim, a, &grid, &P, &ols, st)
 #endif
+#ifdef B200RL_AB_TILE32
                       : update_gemm_launch(MODE_GRAD, obs_dim, h1, act_dim, a, &grid, &P, &ols, st);
+#else
+                      : update_umma64_launch(MODE_GRAD, obs_dim, act_dim, a, &grid, &P, &ols, st);
+#endif
   if (rc) return rc;
   FinArgs f{};
   f.partial = ws; f.nblocks = grid; f.K = P; f.vec_out = g_out;
@@ -188,7 +192,7 @@ int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim
   int rc = (h1 == 32) ? ((h_cache != nullptr) ? update_umma32_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st)
                                               : update_tile_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st))
 #endif
-           : (h_cache != nullptr) ? update_umma_fvp_launch(obs_dim, act_dim, a, &grid, &P, &ols, st)
+           : (h_cache != nullptr) ? update_umma64_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st)
                                   : update_gemm_launch(MODE_FVP, obs_dim, h1, act_dim, a, &grid, &P, &ols, st);
   if (rc) return rc;
   FinArgs f{};

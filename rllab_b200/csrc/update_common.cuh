@@ -46,9 +46,10 @@ int update_gemm_launch(int mode, int obs_dim, int h, int act_dim, const UpdArgs&
                        int* ols_out, cudaStream_t st);
 
 
-// 64-wide nets, Fisher-vector product with cached activations: dense layer chain on the tensor cores (update_umma.cu)
-int update_umma_fvp_launch(int obs_dim, int act_dim, const UpdArgs& a, int* grid_out, int* P_out, int* ols_out,
-                           cudaStream_t st);
+// 64-wide nets, gradient and (with cached activations) Fisher-vector product: dense layer chain on the tensor cores
+// (update_umma.cu); same contract as update_tile_launch.
+int update_umma64_launch(int mode, int obs_dim, int act_dim, const UpdArgs& a, int* grid_out, int* P_out, int* ols_out,
+                         cudaStream_t st);
 
 
 // 32-wide nets, gradient and (with cached activations) Fisher-vector product: dense layer chain on the tensor cores

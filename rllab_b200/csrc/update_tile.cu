@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(T_THREADS, tile_minblocks<N, MODE>()) update_t
     tile_phase_a<N, MODE, SM, LD>(a, sp, sv, stage, D, inrange ? s : a.B - 1, inrange, valid, tid, s_loss, s_kl, m_kl);
     __syncthreads();
     // ================= phase B: Gram accumulation over the tile (tile_gram.cuh)
-    gram.accumulate(stage, tid);
+    gram.accumulate_a(stage, tid);
+    gram.accumulate_b(stage, tid);
     __syncthreads();
   }
 

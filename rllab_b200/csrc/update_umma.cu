@@ -1,6 +1,11 @@
-// Fisher-vector product for 64-wide policies with the dense layer chain on the 5th-generation tensor cores
-// (tcgen05.mma.kind::tf32, accumulators and A operands in TMEM).  north_star: "tensor cores only for the dense policy
-// GEMM where hidden_dim >= 64".
+// Surrogate gradient and Fisher-vector product for 64-wide policies with the dense layer chain on the 5th-generation
+// tensor cores (tcgen05.mma.kind::tf32, accumulators and A operands in TMEM).  north_star: "tensor cores only for the dense
+// policy GEMM where hidden_dim >= 64".
+//
+// The description below is the Fisher-vector pass (MODE_FVP).  The gradient pass (MODE_GRAD) runs the same pipeline with
+// the forward chain in place of the tangent chain: B  H1pre = X W0;  C  h1 = tanh(H1pre + b0) -> TMEM (and the activation
+// cache);  D  H2pre = H1 W1;  E  h2 = tanh(H2pre + b1), mean, log-likelihood, surrogate / KL terms, dmu, dlog_std, d2;
+// F, G, H as below.  Its forward is float32-grade, not bit-identical to the FFMA chain of the rollout (update_umma32.cu).
 //
 // Per 128-sample tile (one CTA of 256 threads per SM, persistent over tiles; samples = the 128 TMEM lanes):
 //   A   load X and the cached activations H1, H2 (written by b200rl_grad at the same theta); H1 / X -> TMEM A operands
@@ -39,18 +44,20 @@ constexpr int U_cACC_A = 0, U_cACC_B = 64, U_cX_HI = 128, U_cX_LO = 152, U_cH1_H
               U_cT_LO = 384;
 constexpr int U_KX = 24;   // obs columns of the X operand (O <= 20 padded with zeros to a multiple of 8)
 
-template <class N>
+template <class N, int MODE>
 struct UmmaSmem {
   static constexpr int O = N::O, H = 64, A = N::A;
   static_assert(N::H1 == 64 && N::H2 == 64 && O <= U_KX, "tcgen05 Fisher-vector kernel: (64,64) nets, obs_dim <= 24");
   static constexpr int IMG64 = 64 * 64 * 4, IMGX = 64 * U_KX * 4;            // bytes of one [64 x K] operand image
-  // weight images (hi then lo): bW1T [j][i], bV1T [j][i], bW1 [i][j], bV0T [j][o]
-  static constexpr int o_bW1T = 0, o_bV1T = o_bW1T + 2 * IMG64, o_bW1 = o_bV1T + 2 * IMG64, o_bV0T = o_bW1 + 2 * IMG64;
-  static constexpr int o_small = o_bV0T + 2 * IMGX;                           // floats: Wout, Vout, vb0, vb1, vbout
+  // weight images (hi then lo): bW1T [j][i], bV1T [j][i] (FVP only), bW1 [i][j], bV0T [j][o] (GRAD: W0^T)
+  static constexpr int o_bW1T = 0, o_bV1T = o_bW1T + 2 * IMG64, o_bW1 = o_bV1T + (MODE == MODE_FVP ? 2 * IMG64 : 0),
+                       o_bV0T = o_bW1 + 2 * IMG64;
+  static constexpr int o_small = o_bV0T + 2 * IMGX;          // floats: Wout, Vout, vb0 | b0, vb1 | b1, vbout | bout
   static constexpr int n_small = ((2 * H * A + 2 * H + A + 3) / 4) * 4;
   static constexpr int o_stage = o_small + n_small * 4;
   static constexpr int rX = 0, rH1 = rX + O, rD1 = rH1 + H, rD2 = rD1 + H, R = rD2 + H;
-  static constexpr int o_bar = ((o_stage + R * U_LD * 4 + 15) / 16) * 16;
+  static constexpr int o_red = ((o_stage + R * U_LD * 4 + 15) / 16) * 16;     // 3 x 32 doubles: loss / KL block reduction
+  static constexpr int o_bar = o_red + 3 * 32 * 8;
   static constexpr size_t bytes = (size_t)o_bar + 64;
   static_assert(bytes <= 232448, "does not fit the 227 KB of shared memory");
 };
@@ -58,14 +65,15 @@ struct UmmaSmem {
 // element (n, k) of a K-major [64 x K] image, byte offset
 __device__ __forceinline__ int u_boff(int n, int k) { return (k & 3) * 4 + (n & 7) * 16 + (n >> 3) * 128 + (k >> 2) * 1024; }
 
-template <class N>
-__global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
-  using SM = UmmaSmem<N>;
+template <class N, int MODE>
+__global__ void __launch_bounds__(U_THREADS, 1) update_umma64_kernel(UpdArgs a) {
+  using SM = UmmaSmem<N, MODE>;
   constexpr int O = N::O, H = 64, A = N::A, P = N::P, LD = U_LD;
   extern __shared__ __align__(1024) unsigned char smem[];
   float* small = reinterpret_cast<float*>(smem + SM::o_small);
   float* sWout = small, *sVout = small + H * A, *svb0 = small + 2 * H * A, *svb1 = svb0 + H, *svbo = svb1 + H;
   float* stage = reinterpret_cast<float*>(smem + SM::o_stage);
+  double* red_scratch = reinterpret_cast<double*>(smem + SM::o_red);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::o_bar);           // [3] mbarriers, then the TMEM base holder
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + SM::o_bar + 32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -76,31 +84,36 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
   // ---- one-time setup: operand images of the weights, small parameters, barriers, TMEM
   for (int e = tid; e < H * H; e += U_THREADS) {
     const int i = e / H, j = e % H;                                         // W1[i][j] (row-major in theta)
-    const float w = a.params[N::oW1 + e], v = (float)a.xvec[N::oW1 + e];
-    const float wh = tf32_hi(w), vh = tf32_hi(v);
+    const float w = a.params[N::oW1 + e];
+    const float wh = tf32_hi(w);
     *reinterpret_cast<float*>(smem + SM::o_bW1T + u_boff(j, i)) = wh;
     *reinterpret_cast<float*>(smem + SM::o_bW1T + SM::IMG64 + u_boff(j, i)) = w - wh;
-    *reinterpret_cast<float*>(smem + SM::o_bV1T + u_boff(j, i)) = vh;
-    *reinterpret_cast<float*>(smem + SM::o_bV1T + SM::IMG64 + u_boff(j, i)) = v - vh;
+    if constexpr (MODE == MODE_FVP) {
+      const float v = (float)a.xvec[N::oW1 + e];
+      const float vh = tf32_hi(v);
+      *reinterpret_cast<float*>(smem + SM::o_bV1T + u_boff(j, i)) = vh;
+      *reinterpret_cast<float*>(smem + SM::o_bV1T + SM::IMG64 + u_boff(j, i)) = v - vh;
+    }
     *reinterpret_cast<float*>(smem + SM::o_bW1 + u_boff(i, j)) = wh;
     *reinterpret_cast<float*>(smem + SM::o_bW1 + SM::IMG64 + u_boff(i, j)) = w - wh;
   }
   for (int e = tid; e < U_KX * H; e += U_THREADS) {
     const int o = e / H, j = e % H;
-    const float v = o < O ? (float)a.xvec[N::oW0 + o * H + j] : 0.f;
+    float v = 0.f;
+    if (o < O) v = (MODE == MODE_FVP) ? (float)a.xvec[N::oW0 + o * H + j] : a.params[N::oW0 + o * H + j];
     const float vh = tf32_hi(v);
     *reinterpret_cast<float*>(smem + SM::o_bV0T + u_boff(j, o)) = vh;
     *reinterpret_cast<float*>(smem + SM::o_bV0T + SM::IMGX + u_boff(j, o)) = v - vh;
   }
   for (int e = tid; e < H * A; e += U_THREADS) {
     sWout[e] = a.params[N::oWo + e];
-    sVout[e] = (float)a.xvec[N::oWo + e];
+    sVout[e] = (MODE == MODE_FVP) ? (float)a.xvec[N::oWo + e] : 0.f;
   }
-  for (int e = tid; e < H; e += U_THREADS) {
-    svb0[e] = (float)a.xvec[N::ob0 + e];
-    svb1[e] = (float)a.xvec[N::ob1 + e];
+  for (int e = tid; e < H; e += U_THREADS) {      // GRAD: the biases themselves
+    svb0[e] = (MODE == MODE_FVP) ? (float)a.xvec[N::ob0 + e] : a.params[N::ob0 + e];
+    svb1[e] = (MODE == MODE_FVP) ? (float)a.xvec[N::ob1 + e] : a.params[N::ob1 + e];
   }
-  if (tid < A) svbo[tid] = (float)a.xvec[N::obo + tid];
+  if (tid < A) svbo[tid] = (MODE == MODE_FVP) ? (float)a.xvec[N::obo + tid] : a.params[N::obo + tid];
   double* out = a.partial + (size_t)blockIdx.x * P;
   for (int i = tid; i < P; i += U_THREADS) out[i] = 0.0;
   if (tid == 0) {
@@ -120,13 +133,8 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
   const uint32_t tbase = *tmem_holder;
   const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);                 // this warp's 32 lanes
 
-  float Mmu[A];
-#pragma unroll
-  for (int k = 0; k < A; ++k) {
-    const float ls = clamp_log_std(a.params[N::ols + k], a.log_min_std);
-    const float sd = expf(ls);
-    Mmu[k] = 2.0f / (2.0f * sd * sd + 1e-8f);
-  }
+  TileDist D;
+  tile_dist_init<N, MODE>(D, a.params + N::ols, a);
   const uint64_t dW1T_hi = u_desc(u_smem_u32(smem + SM::o_bW1T), 1024, 128), dW1T_lo = u_desc(u_smem_u32(smem + SM::o_bW1T + SM::IMG64), 1024, 128);
   const uint64_t dV1T_hi = u_desc(u_smem_u32(smem + SM::o_bV1T), 1024, 128), dV1T_lo = u_desc(u_smem_u32(smem + SM::o_bV1T + SM::IMG64), 1024, 128);
   const uint64_t dW1_hi = u_desc(u_smem_u32(smem + SM::o_bW1), 1024, 128), dW1_lo = u_desc(u_smem_u32(smem + SM::o_bW1 + SM::IMG64), 1024, 128);
@@ -158,9 +166,10 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
 #pragma unroll
   for (int k = 0; k <= OH; ++k) gS[k] = make_float2(0.f, 0.f);
   float gWo[3] = {0.f, 0.f, 0.f};      // this lane's 3 entries of the warp's 32 x 3 block of dWout (reduce-scatter owner)
-  float gbo[A];
+  float gbo[A], gls[A];               // dbout, dlog_std (GRAD): lane 0 of the unit-half-0 warps
 #pragma unroll
-  for (int k = 0; k < A; ++k) gbo[k] = 0.f;
+  for (int k = 0; k < A; ++k) { gbo[k] = 0.f; gls[k] = 0.f; }
+  double s_loss = 0.0, s_kl = 0.0, m_kl = -1.0e300;   // GRAD: surrogate / KL terms, counted by the unit-half-0 thread
   // flat index (j_local * 3 + k) of gWo[r]: the reduce-scatter keeps the lower / upper half by lane bits 4..0
   const int wo_base = ((lane >> 4) & 1) * 48 + ((lane >> 3) & 1) * 24 + ((lane >> 2) & 1) * 12 + ((lane >> 1) & 1) * 6 +
                       (lane & 1) * 3;
@@ -207,6 +216,10 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
     if (lane == 0)
 #pragma unroll
       for (int k = 0; k < A; ++k) scr[warp * 100 + 96 + k] = gbo[k];
+    float* scl = scr + 8 * 100;                 // [4 quadrant warps of unit half 0][A]: dlog_std partial sums
+    if (MODE == MODE_GRAD && lane == 0 && hf == 0)
+#pragma unroll
+      for (int k = 0; k < A; ++k) scl[q * 4 + k] = gls[k];
     __syncthreads();
     if (tid < 2 * 96) {
       const int h2 = tid / 96, f = tid % 96;   // unit half, flat (j_local, k) index
@@ -218,11 +231,14 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
     } else if (tid < 2 * 96 + A) {
       const int k = tid - 2 * 96;
       out[N::obo + k] += (double)((scr[0 * 100 + 96 + k] + scr[1 * 100 + 96 + k]) + (scr[2 * 100 + 96 + k] + scr[3 * 100 + 96 + k]));
+    } else if (MODE == MODE_GRAD && tid < 2 * 96 + 2 * A) {
+      const int k = tid - 2 * 96 - A;
+      out[N::ols + k] += (double)((scl[0 * 4 + k] + scl[1 * 4 + k]) + (scl[2 * 4 + k] + scl[3 * 4 + k]));
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r) gWo[r] = 0.f;
 #pragma unroll
-    for (int k = 0; k < A; ++k) gbo[k] = 0.f;
+    for (int k = 0; k < A; ++k) { gbo[k] = 0.f; gls[k] = 0.f; }
     __syncthreads();
   };
 
@@ -260,21 +276,23 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
         asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(tlane + U_cX_LO + 16),
                      "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
       }
-      const float* hc = a.h_cache + sl;
+      if constexpr (MODE == MODE_FVP) {
+        const float* hc = a.h_cache + sl;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        h1[c] = hc[(size_t)(j0 + c) * a.B];
-        h2[c] = hc[(size_t)(H + j0 + c) * a.B];
-      }
+        for (int c = 0; c < 32; ++c) {
+          h1[c] = hc[(size_t)(j0 + c) * a.B];
+          h2[c] = hc[(size_t)(H + j0 + c) * a.B];
+        }
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        stage[(SM::rH1 + j0 + c) * LD + srow] = h1[c];
-        const float hh = tf32_hi(h1[c]);
-        hi[c] = __float_as_uint(hh);
-        lo[c] = __float_as_uint(h1[c] - hh);
+        for (int c = 0; c < 32; ++c) {
+          stage[(SM::rH1 + j0 + c) * LD + srow] = h1[c];
+          const float hh = tf32_hi(h1[c]);
+          hi[c] = __float_as_uint(hh);
+          lo[c] = __float_as_uint(h1[c] - hh);
+        }
+        u_st32(tlane + U_cH1_HI + j0, hi);
+        u_st32(tlane + U_cH1_LO + j0, lo);
       }
-      u_st32(tlane + U_cH1_HI + j0, hi);
-      u_st32(tlane + U_cH1_LO + j0, lo);
       u_wait_st();
     }
     u_fence_before();
@@ -282,9 +300,19 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
     // ================= B: T1pre = X V0 ; T2pre = H1 V1
     if (tid == 0) {
       u_fence_after();
-      split_gemm(U_cACC_A, U_cX_HI, U_cX_LO, dV0T_hi, dV0T_lo, U_KX / 8, false);
+      split_gemm(U_cACC_A, U_cX_HI, U_cX_LO, dV0T_hi, dV0T_lo, U_KX / 8, false);     // X V0  |  GRAD: X W0
       u_commit(&bars[0]);
-      split_gemm(U_cACC_B, U_cH1_HI, U_cH1_LO, dV1T_hi, dV1T_lo, 8, false);
+      if constexpr (MODE == MODE_FVP) split_gemm(U_cACC_B, U_cH1_HI, U_cH1_LO, dV1T_hi, dV1T_lo, 8, false);
+    }
+    // GRAD: the remaining per-sample inputs, requested while the first GEMM runs
+    float act[A], om[A], adv_s = 0.f;
+    if constexpr (MODE == MODE_GRAD) {
+#pragma unroll
+      for (int k = 0; k < A; ++k) {
+        act[k] = a.act[(size_t)k * a.B + sl];
+        om[k] = a.old_mean[(size_t)k * a.B + sl];
+      }
+      adv_s = a.adv[sl];
     }
     // ================= C: T1 = (T1pre + vb0)(1 - H1^2) -> TMEM A operand
     timed_out |= !u_wait(&bars[0], phase);
@@ -294,7 +322,15 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
       u_ld32(tlane + U_cACC_A + j0, r);
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const float t1 = (__uint_as_float(r[c]) + svb0[j0 + c]) * (1.0f - h1[c] * h1[c]);
+        float t1;                                 // the next A operand: t1 (FVP) | h1 (GRAD)
+        if constexpr (MODE == MODE_FVP) {
+          t1 = (__uint_as_float(r[c]) + svb0[j0 + c]) * (1.0f - h1[c] * h1[c]);
+        } else {
+          t1 = tanh_f(__uint_as_float(r[c]) + svb0[j0 + c]);
+          h1[c] = t1;
+          stage[(SM::rH1 + j0 + c) * LD + srow] = t1;
+          if (a.h_cache != nullptr && s < a.B) a.h_cache[(size_t)(j0 + c) * a.B + s] = t1;
+        }
         const float th = tf32_hi(t1);
         r[c] = __float_as_uint(th);
         lo[c] = __float_as_uint(t1 - th);
@@ -308,7 +344,7 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
     // ================= D: T2pre += T1 W1
     if (tid == 0) {
       u_fence_after();
-      split_gemm(U_cACC_B, U_cT_HI, U_cT_LO, dW1T_hi, dW1T_lo, 8, true);
+      split_gemm(U_cACC_B, U_cT_HI, U_cT_LO, dW1T_hi, dW1T_lo, 8, MODE == MODE_FVP);   // += T1 W1  |  GRAD: H1 W1
       u_commit(&bars[1]);
     }
     // ================= E: T2, mu_dot, dmu, D2 (+ dWout / dbout partial sums)
@@ -322,21 +358,64 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
       for (int k = 0; k < A; ++k) md[k] = 0.f;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const float t2 = (__uint_as_float(r[c]) + svb1[j0 + c]) * (1.0f - h2[c] * h2[c]);
+        if constexpr (MODE == MODE_FVP) {
+          const float t2 = (__uint_as_float(r[c]) + svb1[j0 + c]) * (1.0f - h2[c] * h2[c]);
 #pragma unroll
-        for (int k = 0; k < A; ++k)
-          md[k] = fmaf(t2, sWout[(j0 + c) * A + k], fmaf(h2[c], sVout[(j0 + c) * A + k], md[k]));
+          for (int k = 0; k < A; ++k)
+            md[k] = fmaf(t2, sWout[(j0 + c) * A + k], fmaf(h2[c], sVout[(j0 + c) * A + k], md[k]));
+        } else {
+          h2[c] = tanh_f(__uint_as_float(r[c]) + svb1[j0 + c]);
+          if (a.h_cache != nullptr && s < a.B) a.h_cache[(size_t)(H + j0 + c) * a.B + s] = h2[c];
+#pragma unroll
+          for (int k = 0; k < A; ++k) md[k] = fmaf(h2[c], sWout[(j0 + c) * A + k], md[k]);   // this half's part of the mean
+        }
       }
       // the two unit halves of a sample live in warps q and q + 4: exchange the partial sums through the idle D1 rows
       float* xch = stage + SM::rD1 * LD;       // [2][128][4]
 #pragma unroll
       for (int k = 0; k < A; ++k) xch[(hf * U_TILE + srow) * 4 + k] = md[k];
       __syncthreads();
-      float dmu[A];
+      float dmu[A], dl[A];
+      if constexpr (MODE == MODE_FVP) {
 #pragma unroll
-      for (int k = 0; k < A; ++k) {
-        const float m = svbo[k] + (xch[srow * 4 + k] + xch[(U_TILE + srow) * 4 + k]);
-        dmu[k] = valid ? m * Mmu[k] : 0.f;
+        for (int k = 0; k < A; ++k) {
+          const float m = svbo[k] + (xch[srow * 4 + k] + xch[(U_TILE + srow) * 4 + k]);
+          dmu[k] = valid ? m * D.Mmu[k] : 0.f;
+          dl[k] = 0.f;
+        }
+      } else {
+        // both unit halves of a sample evaluate the (cheap) distribution math; the half-0 thread counts the sample
+        float z[A], zsq = 0.f, zsq_old = 0.f, kl = 0.f;
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          const float mu = svbo[k] + (xch[srow * 4 + k] + xch[(U_TILE + srow) * 4 + k]);
+          z[k] = (act[k] - mu) * D.inv_std[k];
+          zsq += z[k] * z[k];
+          const float zo = (act[k] - om[k]) * D.inv_std_old[k];
+          zsq_old += zo * zo;
+          const float dm = om[k] - mu;
+          kl += (dm * dm + D.var_old[k] - D.var_new[k]) / D.var_new2[k] + D.ls_new[k] - D.ls_old[k];
+        }
+        const float logp_new = -D.sum_ls_new - 0.5f * zsq - D.half_log2pi_A;
+        float w_s, term;
+        if (a.loss_kind == B200RL_LOSS_TRPO) {
+          const float logp_old = -D.sum_ls_old - 0.5f * zsq_old - D.half_log2pi_A;
+          w_s = expf(logp_new - logp_old) * adv_s;
+          term = -w_s;
+        } else {
+          w_s = adv_s;
+          term = -logp_new * adv_s;
+        }
+        if (!valid) { w_s = 0.f; term = 0.f; }
+        if (hf == 0) {
+          s_loss += (double)term;
+          if (valid) { s_kl += (double)kl; m_kl = fmax(m_kl, (double)kl); }
+        }
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          dmu[k] = -w_s * z[k] * D.inv_std[k];
+          dl[k] = -w_s * (z[k] * z[k] - 1.0f);
+        }
       }
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
@@ -399,6 +478,10 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
         for (int k = 0; k < A; ++k) {
           const float sdm = warp_sum(dmu[k]);
           if (lane == 0) gbo[k] += sdm;
+          if constexpr (MODE == MODE_GRAD) {
+            const float sdl = warp_sum(dl[k]);
+            if (lane == 0) gls[k] += sdl;
+          }
         }
       }
     }
@@ -429,10 +512,12 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
         const long long ns = tile_at(a, nti) * U_TILE + q * 32;      // one 128 B line per (row, warp): lane 0 fetches it
         if (lane == 0 && ns < a.B) {
           const float* hcn = a.h_cache + ns;
+          if constexpr (MODE == MODE_FVP) {
 #pragma unroll 8
-          for (int c = 0; c < 32; ++c) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(hcn + (size_t)(j0 + c) * a.B));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(hcn + (size_t)(H + j0 + c) * a.B));
+            for (int c = 0; c < 32; ++c) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(hcn + (size_t)(j0 + c) * a.B));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(hcn + (size_t)(H + j0 + c) * a.B));
+            }
           }
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
@@ -484,32 +569,41 @@ __global__ void __launch_bounds__(U_THREADS, 1) fvp_umma_kernel(UpdArgs a) {
   }
   if (since_flush > 0) flush();
   if (timed_out) out[tid % P] = __longlong_as_double(0x7FF8000000000000ll);   // an MMA never completed: poison the result
+  if constexpr (MODE == MODE_GRAD) {
+    __syncthreads();
+    double v[2] = {s_loss, s_kl};
+    double mx[1] = {m_kl};
+    double* sc = a.partial + (size_t)gridDim.x * P + (size_t)blockIdx.x * 3;
+    block_reduce_store<2, false>(v, red_scratch, sc);
+    block_reduce_store<1, true>(mx, red_scratch, sc + 2);
+  }
   u_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(U_TMEM_COLS));
 }
 
-template <class N>
+template <class N, int MODE>
 static int launch_umma(const UpdArgs& a, int* grid_out, cudaStream_t st) {
-  using SM = UmmaSmem<N>;
-  B200RL_SET_MAX_SMEM((fvp_umma_kernel<N>), SM::bytes);
+  using SM = UmmaSmem<N, MODE>;
+  B200RL_SET_MAX_SMEM((update_umma64_kernel<N, MODE>), SM::bytes);
   long long grid = num_sms();                      // one CTA per SM (512 TMEM columns, 220 KB of shared memory)
   const long long ntiles = host_n_tiles(a, U_TILE);
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
-  fvp_umma_kernel<N><<<(unsigned)grid, U_THREADS, SM::bytes, st>>>(a);
-  B200RL_LAUNCH_CHECK("fvp_umma_kernel");
+  update_umma64_kernel<N, MODE><<<(unsigned)grid, U_THREADS, SM::bytes, st>>>(a);
+  B200RL_LAUNCH_CHECK("update_umma64_kernel");
   *grid_out = (int)grid;
   return 0;
 }
 
-int update_umma_fvp_launch(int obs_dim, int act_dim, const UpdArgs& a, int* grid_out, int* P_out, int* ols_out,
-                           cudaStream_t st) {
+int update_umma64_launch(int mode, int obs_dim, int act_dim, const UpdArgs& a, int* grid_out, int* P_out, int* ols_out,
+                         cudaStream_t st) {
   const int h1 = 64, h2 = 64;
   B200RL_DISPATCH_NET_H(64, {
     *P_out = NetT::P;
     *ols_out = NetT::ols;
-    int rc = launch_umma<NetT>(a, grid_out, st);
+    int rc = (mode == MODE_GRAD) ? launch_umma<NetT, MODE_GRAD>(a, grid_out, st)
+                                 : launch_umma<NetT, MODE_FVP>(a, grid_out, st);
     if (rc) return rc;
   });
   return 0;

@@ -34,15 +34,22 @@
 namespace b200rl {
 
 constexpr int V_THREADS = 128, V_TILE = 128, V_LD = V_TILE + 4;
+#ifndef B200RL_V_PACKED_GRAM
+#define B200RL_V_PACKED_GRAM 1          // dW1 Gram with packed FFMA2 (A/B on a B200: see DESIGN.md)
+#endif
+#ifndef B200RL_V_MAXB
+#define B200RL_V_MAXB 3                 // resident CTAs per SM where shared memory / TMEM / registers allow
+#endif
 
 template <class N, int MODE>
 struct Umma32 {
   static constexpr int O = N::O, H = 32, A = N::A;
   static_assert(N::H1 == 32 && N::H2 == 32 && O <= 24, "tcgen05 32-wide kernel: (32,32) nets, obs_dim <= 24");
   static constexpr int KX = ((O + 7) / 8) * 8;                 // obs columns of the X operand, zero padded
-  // TMEM columns (float32 each): accumulators, X hi/lo, one A-operand slot (H1, then T1 / D2) hi/lo
-  static constexpr int cACC_A = 0, cACC_B = 32, cX_HI = 64, cX_LO = cX_HI + KX, cOP_HI = cX_LO + KX, cOP_LO = cOP_HI + 32,
-                       cEND = cOP_LO + 32;
+  // TMEM columns (float32 each): accumulators (the gradient pass uses them strictly one after the other: one slot), X
+  // hi/lo, one A-operand slot (H1, then T1 / D2) hi/lo
+  static constexpr int cACC_A = 0, cACC_B = (MODE == MODE_GRAD) ? 0 : 32, cX_HI = cACC_B + 32, cX_LO = cX_HI + KX,
+                       cOP_HI = cX_LO + KX, cOP_LO = cOP_HI + 32, cEND = cOP_LO + 32;
   static constexpr int TMEM_COLS = cEND <= 128 ? 128 : 256;
   static constexpr int IMG = 32 * 32 * 4, IMGX = 32 * KX * 4;   // bytes of one [32 x K] operand image
   // weight images (hi then lo).  GRAD: W0^T [j][o], W1^T [j][i], W1 [i][j].  FVP: V0^T, V1^T, W1^T, W1.
@@ -51,13 +58,19 @@ struct Umma32 {
   // small parameters (floats): GRAD b0[32] b1[32] Wout[32A] bout[A];  FVP vb0[32] vb1[32] Wout[32A] Vout[32A] vbout[A]
   static constexpr int n_small = ((64 + 2 * H * A + A + 3) / 4) * 4;
   static constexpr int o_small = o_img_end, o_stage = o_small + n_small * 4;
-  static constexpr int rX = 0, rH1 = rX + O, rH2 = rH1 + H, rD1 = rH2 + H, rD2 = rD1 + H, rDM = rD2 + H, rDL = rDM + A,
+  // stage rows; D1 reuses the H2 rows (H2 is dead once part A of the Gram phase has run, D1 only exists after it)
+  static constexpr int rX = 0, rH1 = rX + O, rH2 = rH1 + H, rD1 = rH2, rD2 = rH2 + H, rDM = rD2 + H, rDL = rDM + A,
                        R = rDL + A;
   static constexpr int o_red = ((o_stage + R * V_LD * 4 + 15) / 16) * 16;   // 3 x 32 doubles of reduction scratch
   static constexpr int o_bar = o_red + 3 * 32 * 8;
   static constexpr size_t bytes = (size_t)o_bar + 64;
   static_assert(2 * 64 * 16 * 8 <= R * V_LD * 4, "stage region must hold the K-half combine scratch");
   static_assert(bytes <= 232448, "does not fit the 227 KB of shared memory");
+  // resident CTAs per SM: shared memory (228 KB, 1 KB reserved per CTA), TMEM (512 columns), registers (64 K / 128 threads)
+  static constexpr int by_smem = (int)((228 * 1024) / (bytes + 1024)), by_tmem = 512 / TMEM_COLS;
+  static constexpr int MINB = (by_smem < by_tmem ? by_smem : by_tmem) < B200RL_V_MAXB
+                                  ? ((by_smem < by_tmem ? by_smem : by_tmem) < 1 ? 1 : (by_smem < by_tmem ? by_smem : by_tmem))
+                                  : B200RL_V_MAXB;
 };
 
 // element (n, k) of a K-major [32 x K] image, byte offset
@@ -69,7 +82,7 @@ __device__ __forceinline__ void v_st8(uint32_t taddr, const uint32_t* r) {
 }
 
 template <class N, int MODE>
-__global__ void __launch_bounds__(V_THREADS, 2) update_umma32_kernel(UpdArgs a) {
+__global__ void __launch_bounds__(V_THREADS, (Umma32<N, MODE>::MINB)) update_umma32_kernel(UpdArgs a) {
   using SM = Umma32<N, MODE>;
   constexpr int O = N::O, H = 32, A = N::A, P = N::P, LD = V_LD, KX = SM::KX;
   constexpr uint32_t IDESC = u_idesc(128, 32);
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(V_THREADS, 2) update_umma32_kernel(UpdArgs a) 
     u_wait_st();
   };
 
-  TileGram<N, SM::rX, SM::rH1, SM::rH2, SM::rD1, SM::rD2, SM::rDM, LD> gram;
+  TileGram<N, SM::rX, SM::rH1, SM::rH2, SM::rD1, SM::rD2, SM::rDM, LD, B200RL_V_PACKED_GRAM != 0> gram;
   gram.init();
   double s_loss = 0.0, s_kl = 0.0, m_kl = -1.0e300;
   bool timed_out = false;
@@ -359,6 +372,9 @@ __global__ void __launch_bounds__(V_THREADS, 2) update_umma32_kernel(UpdArgs a) 
       split_gemm(SM::cACC_A, SM::cOP_HI, SM::cOP_LO, dW1_hi, dW1_lo, 4, false);                 // D2 W1^T
       u_commit(&bars[2]);
     }
+    // ================= Gram part A behind the last GEMM: dW1 = H1^T D2, dWout, db1, dbout, dlog_std (tile_gram.cuh)
+    gram.accumulate_a(stage, tid);
+    __syncthreads();                       // every thread is done with the H2 rows: D1 may overwrite them
     timed_out |= !u_wait(&bars[2], phase);
     u_fence_after();
     // ================= E3 / G: d1 = D1pre (1 - h1^2)
@@ -370,8 +386,8 @@ __global__ void __launch_bounds__(V_THREADS, 2) update_umma32_kernel(UpdArgs a) 
     }
     u_fence_before();
     __syncthreads();
-    // ================= Gram products over the tile (FP32 pipe, tile_gram.cuh)
-    gram.accumulate(stage, tid);
+    // ================= Gram part B: dW0 = X^T D1, db0
+    gram.accumulate_b(stage, tid);
     __syncthreads();
   }
 
@@ -395,12 +411,7 @@ template <class N, int MODE>
 static int launch_umma32(const UpdArgs& a, int* grid_out, cudaStream_t st) {
   using SM = Umma32<N, MODE>;
   B200RL_SET_MAX_SMEM((update_umma32_kernel<N, MODE>), SM::bytes);
-  int per_sm = (int)((228 * 1024) / (SM::bytes + 1024));   // 228 KB per SM, 1 KB reserved per resident CTA
-  const int tmem_per_sm = 512 / SM::TMEM_COLS;             // every resident CTA must get its TMEM columns
-  if (per_sm > tmem_per_sm) per_sm = tmem_per_sm;
-  if (per_sm > 2) per_sm = 2;
-  if (per_sm < 1) per_sm = 1;
-  long long grid = (long long)num_sms() * per_sm;
+  long long grid = (long long)num_sms() * SM::MINB;        // persistent: every CTA resident, with its TMEM columns
   const long long ntiles = host_n_tiles(a, V_TILE);
   if (grid > ntiles) grid = ntiles;
   if (grid > MAX_PARTIAL_BLOCKS) grid = MAX_PARTIAL_BLOCKS;

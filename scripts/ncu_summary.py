@@ -15,9 +15,9 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
            "sm__inst_executed_pipe_fma.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]
-SHORT = {"update_tile_kernel": "grad", "rollout_kernel": "rollout", "loss_thread_kernel": "loss_kl",
-         "process_samples_kernel": "process_samples", "lfb_gram": "lfb_gram", "fvp_umma_kernel": "fvp",
-         "update_gemm_kernel": "grad"}
+SHORT = {"update_umma32_kernel": "grad", "update_tile_kernel": "grad", "rollout_kernel": "rollout",
+         "loss_thread_kernel": "loss_kl", "gae_scan_kernel": "process_samples", "lfb_gram": "lfb_gram",
+         "update_umma64_kernel": "fvp", "update_gemm_kernel": "grad"}
 
 
 def raw_rows(rep):

@@ -7,10 +7,10 @@ mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra > gpurun_out/bench_under_ncu_r02.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:'update_tile_kernel|loss_thread_kernel|rollout_kernel|process_samples_kernel|lfb_gram' \
+    -k regex:'update_umma32_kernel|loss_thread_kernel|rollout_kernel|gae_scan_kernel|lfb_predict_kernel|lfb_gram' \
     -s 5 -c 5 -o gpurun_out/prof_r02_cfg2 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extra \
     > gpurun_out/ncu_full_r02_cfg2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'fvp_umma_kernel|update_gemm_kernel' -s 2 -c 3 \
+ncu --set full --clock-control none --import-source on -k regex:'update_umma64_kernel' -s 2 -c 3 \
     -o gpurun_out/prof_r02_hopper -f python bench.py --workload hopper_trpo_4096x500 --steps 1 --warmup 1 \
     --no-cpu-baseline --no-extra > gpurun_out/ncu_full_r02_hopper.log 2>&1
 ls -la gpurun_out | tail -6

@@ -57,7 +57,7 @@ def main():
     full = make_batch(N * W, 0, N * W)
     ops.center_advantages(full, True, False)
     mine = make_batch(N, comm.rank * N, N * W)
-    mine.adv.copy_(full.adv.view(T, N * W)[:, comm.rank * N:(comm.rank + 1) * N].reshape(-1))   # globally centred
+    mine.adv.copy_(full.adv.view(T, N * W)[:, comm.rank * N:(comm.rank + 1) * N])   # globally centred
     mine.B_global = N * W * T
     P_ = dims.P
     th2 = torch.tensor(theta + 0.02 * np.random.RandomState(9).randn(P_), dtype=torch.float32, device=dev)

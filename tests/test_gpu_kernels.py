@@ -405,9 +405,14 @@ def _check_update_kernels(dev, env_name, hidden, N, T):
         g = torch.zeros(dims.P, dtype=torch.float64, device=dev)
         out_g = torch.zeros(3, dtype=torch.float64, device=dev)
         ops.grad(kind, th2_32, dd, 1e-6, b, g, out_g)
-        np.testing.assert_allclose(out_g.cpu().numpy(), o, rtol=1e-5, atol=1e-8)     # fused loss/KL triple
+        og = out_g.cpu().numpy()     # fused loss/KL triple (tensor-core forward for 32-wide nets): same oracle tolerances
+        np.testing.assert_allclose(og[0], ref_loss, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(og[1], mkl, rtol=2e-5, atol=1e-8)
+        np.testing.assert_allclose(og[2], xkl, rtol=1e-4, atol=1e-8)
+        np.testing.assert_allclose(og, o, rtol=1e-4, atol=2e-6)
         ref_g = P.grad_surr(th2, batch, dims, name)
-        np.testing.assert_allclose(g.cpu().numpy(), ref_g, rtol=2e-4, atol=2e-6 * np.abs(ref_g).max() + 1e-9)
+        # three-pass TF32 chain (tensor cores): 4e-7 of the scale of the summands, i.e. a few 1e-6 of the largest entry
+        np.testing.assert_allclose(g.cpu().numpy(), ref_g, rtol=2e-4, atol=5e-6 * np.abs(ref_g).max() + 1e-9)
     # Fisher-vector product at theta_old
     x = rng.randn(dims.P)
     xd = torch.tensor(x, dtype=torch.float64, device=dev)

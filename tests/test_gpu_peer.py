@@ -37,6 +37,6 @@ def test_bench_two_gpus_reproduces_single_process_run():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["n_gpus"] == 2 and line["replicas_identical"] is True
-    assert line["shard_check"]["max_rel_diff_vs_single_process"] < 1e-9
+    assert line["shard_check"]["max_rel_diff_vs_single_process"] < 1e-7
     assert line["collectives_per_step"] == 0 and line["peer_exchanges_per_step"] >= 3       # no NCCL on the critical path
     assert line["transport"].startswith("peer-memory")
