@@ -106,11 +106,15 @@ __global__ void __launch_bounds__(PRED_THREADS) lfb_predict_kernel(int O_rt, lon
   for (long long i = done + gt; i < B; i += stride) base[i] = (float)lfb_predict<OT>(obs, (size_t)B, (size_t)i, O, tstep[i], sw);
 }
 
-// 14 warps of 32 lanes per SM hold cfg2's 65 536 lanes in ONE wave (148 x 14 x 32 = 66 304); 8-step chunks keep the two
-// register buffers + 20 float64 statistics under the 146 registers that allows
-constexpr int SC_CH = 8, SC_THREADS = 32, SC_BLOCKS_PER_SM = 14;
+// 14 warps of 32 lanes per SM hold cfg2's 65 536 lanes in ONE wave (148 x 14 x 32 = 66 304).  The inputs of the next
+// SC_AHEAD chunks of SC_CH steps are staged through a warp-private shared-memory ring with cp.async (LDGSTS, 16 B per
+// lane, 22 lanes per step row: 128 B rew + 128 B base + 64 B tstep + 32 B flags), so the look-ahead (32 steps = 11 KB per
+// warp, 154 KB per SM in flight) does not cost registers; the scan reads its step back with four conflict-free LDS.
+// Lane counts that are not a multiple of 32 (rows not 16 B aligned) take the register double-buffered path.
+constexpr int SC_CH = 8, SC_THREADS = 32, SC_BLOCKS_PER_SM = 14, SC_AHEAD = 4, SC_RING = SC_AHEAD + 1;
+constexpr int SC_ROW_BYTES = 128 + 128 + 64 + 32;        // rew | base | tstep | flags of one step row of a warp
 
-struct ScanChunk {     // one chunk of SC_CH steps of one lane, in registers
+struct ScanChunk {     // one chunk of SC_CH steps of one lane, in registers (unaligned path)
   float rw[SC_CH], bs[SC_CH];
   unsigned int fl[SC_CH];          // flags | (tstep == 0) << 8
 };
@@ -130,13 +134,16 @@ __device__ __forceinline__ void scan_load(ScanChunk& c, int t_hi, int N, int n, 
   }
 }
 
+template <bool STAGED>
 __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM)
     gae_scan_kernel(int N, int T, const float* __restrict__ rew, const float* __restrict__ base,
                     unsigned char* __restrict__ flags, const unsigned short* __restrict__ tstep, double discount,
                     double gl, int drop_cut, float* __restrict__ adv, float* __restrict__ ret,
                     double* __restrict__ partial_sum, double* __restrict__ partial_max) {
-  __shared__ double scratch[B200RL_PS_NSUM * 32];
-  const int n_raw = blockIdx.x * SC_THREADS + threadIdx.x;
+  __shared__ __align__(16) unsigned char ring[STAGED ? SC_RING * SC_CH * SC_ROW_BYTES : 16];
+  const int lane = threadIdx.x;
+  const int n0 = blockIdx.x * SC_THREADS;
+  const int n_raw = n0 + lane;
   const bool lane_ok = n_raw < N;
   const int n = lane_ok ? n_raw : N - 1;          // out-of-range threads shadow the last lane (no stores, no statistics)
   double s[B200RL_PS_NSUM];
@@ -148,59 +155,127 @@ __global__ void __launch_bounds__(SC_THREADS, SC_BLOCKS_PER_SM)
   double a_n = 0.0, r_n = 0.0, u_n = 0.0, b_n = 0.0;
   bool dropped = false;
 
-  auto scan = [&](const ScanChunk& c, int t_hi) {
-#pragma unroll
-    for (int u = 0; u < SC_CH; ++u) {
-      const int t = t_hi - u;
-      if (t < 0) continue;
-      const size_t idx = (size_t)t * N + n;
-      const unsigned int f = c.fl[u];
-      if (f & B200RL_FLAG_END) {
-        a_n = 0.0; r_n = 0.0; u_n = 0.0; b_n = 0.0;
-        dropped = drop_cut && (f & B200RL_FLAG_CUT);
-      }
-      const double r = (double)c.rw[u], b = (double)c.bs[u];
-      a_n = (r + discount * b_n - b) + gl * a_n;          // base.py:59-61, discount_cumsum(deltas, discount*lambda)
-      r_n = r + discount * r_n;                            // discount_cumsum(rewards, discount)
-      u_n = r + u_n;
-      b_n = b;
-      if (!lane_ok) continue;
-      ret[idx] = (float)r_n;
-      if (dropped) {
-        adv[idx] = 0.f;
-        flags[idx] = (unsigned char)((f & 0xFFu) | B200RL_FLAG_MASKED);
-        continue;
-      }
-      adv[idx] = (float)a_n;
-      // statistics use the float64 values (as the reference does)
-      s[0] += a_n; s[1] += a_n * a_n; s[2] += 1.0;
-      s[7] += r_n; s[8] += r_n * r_n; s[9] += b; s[10] += b * b;
-      const double res = r_n - b;
-      s[11] += res; s[12] += res * res;
-      m[2] = fmax(m[2], -a_n); m[3] = fmax(m[3], a_n);
-      if (f & 0x100u) {  // first sample of a path
-        s[3] += 1.0; s[4] += r_n; s[5] += u_n; s[6] += u_n * u_n;
-        m[0] = fmax(m[0], u_n); m[1] = fmax(m[1], -u_n);
-      }
+  // one step of the reverse scan (base.py:57-66): inputs of sample (t, lane) -> adv / ret / statistics
+  auto step = [&](int t, float rwf, float bsf, unsigned int f) {
+    const size_t idx = (size_t)t * N + n;
+    if (f & B200RL_FLAG_END) {
+      a_n = 0.0; r_n = 0.0; u_n = 0.0; b_n = 0.0;
+      dropped = drop_cut && (f & B200RL_FLAG_CUT);
+    }
+    const double r = (double)rwf, b = (double)bsf;
+    a_n = (r + discount * b_n - b) + gl * a_n;          // base.py:59-61, discount_cumsum(deltas, discount*lambda)
+    r_n = r + discount * r_n;                            // discount_cumsum(rewards, discount)
+    u_n = r + u_n;
+    b_n = b;
+    if (!lane_ok) return;
+    ret[idx] = (float)r_n;
+    if (dropped) {
+      adv[idx] = 0.f;
+      flags[idx] = (unsigned char)((f & 0xFFu) | B200RL_FLAG_MASKED);
+      return;
+    }
+    adv[idx] = (float)a_n;
+    // statistics use the float64 values (as the reference does)
+    s[0] += a_n; s[1] += a_n * a_n; s[2] += 1.0;
+    s[7] += r_n; s[8] += r_n * r_n; s[9] += b; s[10] += b * b;
+    const double res = r_n - b;
+    s[11] += res; s[12] += res * res;
+    m[2] = fmax(m[2], -a_n); m[3] = fmax(m[3], a_n);
+    if (f & 0x100u) {  // first sample of a path
+      s[3] += 1.0; s[4] += r_n; s[5] += u_n; s[6] += u_n * u_n;
+      m[0] = fmax(m[0], u_n); m[1] = fmax(m[1], -u_n);
     }
   };
 
-  // the compiler barriers pin the loads of the NEXT chunk ahead of the scan of the current one (ptxas otherwise sinks
-  // them to their first use, which serialises a DRAM round trip per chunk: 0.29 ms instead of 0.1 on cfg2)
-  ScanChunk ca, cb;
-  scan_load(ca, T - 1, N, n, rew, base, flags, tstep);
-  for (int t_hi = T - 1; t_hi >= 0; t_hi -= 2 * SC_CH) {
-    scan_load(cb, t_hi - SC_CH, N, n, rew, base, flags, tstep);
-    asm volatile("" ::: "memory");
-    scan(ca, t_hi);
-    asm volatile("" ::: "memory");
-    scan_load(ca, t_hi - 2 * SC_CH, N, n, rew, base, flags, tstep);
-    asm volatile("" ::: "memory");
-    scan(cb, t_hi - SC_CH);
-    asm volatile("" ::: "memory");
+  if constexpr (STAGED) {
+    // lane role in a step-row copy: which 16 B piece of which array this lane moves
+    const unsigned char* src0;        // address of this lane's piece in row t = 0
+    size_t row_stride;                // bytes between consecutive rows of that array
+    int dst_off;                      // offset of the piece inside a staged row
+    if (lane < 8) {
+      src0 = reinterpret_cast<const unsigned char*>(rew + n0) + lane * 16; row_stride = (size_t)N * 4; dst_off = lane * 16;
+    } else if (lane < 16) {
+      src0 = reinterpret_cast<const unsigned char*>(base + n0) + (lane - 8) * 16; row_stride = (size_t)N * 4;
+      dst_off = 128 + (lane - 8) * 16;
+    } else if (lane < 20) {
+      src0 = reinterpret_cast<const unsigned char*>(tstep + n0) + (lane - 16) * 16; row_stride = (size_t)N * 2;
+      dst_off = 256 + (lane - 16) * 16;
+    } else {
+      src0 = reinterpret_cast<const unsigned char*>(flags + n0) + ((lane - 20) & 1) * 16; row_stride = (size_t)N;
+      dst_off = 320 + ((lane - 20) & 1) * 16;
+    }
+    const bool copier = lane < 22;
+    const unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(ring);
+    auto stage_chunk = [&](int chunk) {            // chunk c covers steps T-1 - c*SC_CH ... (reverse order), ring slot c % SC_RING
+      const int t_hi = T - 1 - chunk * SC_CH;
+      const unsigned int slot = ring_s + (unsigned int)((chunk % SC_RING) * SC_CH * SC_ROW_BYTES);
+      if (copier) {
+#pragma unroll
+        for (int u = 0; u < SC_CH; ++u) {
+          const int t = t_hi - u;
+          if (t >= 0)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot + u * SC_ROW_BYTES + dst_off),
+                         "l"(src0 + (size_t)t * row_stride) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nchunks = (T + SC_CH - 1) / SC_CH;
+#pragma unroll
+    for (int c = 0; c < SC_AHEAD; ++c) stage_chunk(c);           // (empty groups past the end keep the counting uniform)
+    for (int c = 0; c < nchunks; ++c) {
+      stage_chunk(c + SC_AHEAD);
+      asm volatile("cp.async.wait_group %0;" ::"n"(SC_AHEAD) : "memory");   // chunk c has landed
+      __syncwarp();
+      const unsigned char* slot = ring + (c % SC_RING) * SC_CH * SC_ROW_BYTES;
+      const int t_hi = T - 1 - c * SC_CH;
+#pragma unroll
+      for (int u = 0; u < SC_CH; ++u) {
+        const int t = t_hi - u;
+        if (t < 0) break;
+        const unsigned char* row = slot + u * SC_ROW_BYTES;
+        const float rwf = reinterpret_cast<const float*>(row)[lane];
+        const float bsf = reinterpret_cast<const float*>(row + 128)[lane];
+        const unsigned int ts = reinterpret_cast<const unsigned short*>(row + 256)[lane];
+        const unsigned int f = (unsigned int)row[320 + lane] | (ts == 0 ? 0x100u : 0u);
+        step(t, rwf, bsf, f);
+      }
+      __syncwarp();                                // the slot is refilled by the next stage_chunk
+    }
+  } else {
+    // the compiler barriers keep the loads of the NEXT chunk ahead of the scan of the current one
+    auto scan = [&](const ScanChunk& c, int t_hi) {
+#pragma unroll
+      for (int u = 0; u < SC_CH; ++u) {
+        const int t = t_hi - u;
+        if (t >= 0) step(t, c.rw[u], c.bs[u], c.fl[u]);
+      }
+    };
+    ScanChunk ca, cb;
+    scan_load(ca, T - 1, N, n, rew, base, flags, tstep);
+    for (int t_hi = T - 1; t_hi >= 0; t_hi -= 2 * SC_CH) {
+      scan_load(cb, t_hi - SC_CH, N, n, rew, base, flags, tstep);
+      asm volatile("" ::: "memory");
+      scan(ca, t_hi);
+      asm volatile("" ::: "memory");
+      scan_load(ca, t_hi - 2 * SC_CH, N, n, rew, base, flags, tstep);
+      asm volatile("" ::: "memory");
+      scan(cb, t_hi - SC_CH);
+      asm volatile("" ::: "memory");
+    }
   }
-  block_reduce_store<B200RL_PS_NSUM, false>(s, scratch, partial_sum + (size_t)blockIdx.x * B200RL_PS_NSUM);
-  block_reduce_store<B200RL_PS_NMAX, true>(m, scratch, partial_max + (size_t)blockIdx.x * B200RL_PS_NMAX);
+  // the block is one warp: plain warp reductions, lane 0 stores (no shared-memory scratch: the ring owns the budget)
+  static_assert(SC_THREADS == 32, "one warp per block");
+#pragma unroll
+  for (int i = 0; i < B200RL_PS_NSUM; ++i) {
+    const double v = warp_sum(s[i]);
+    if (lane == 0) partial_sum[(size_t)blockIdx.x * B200RL_PS_NSUM + i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < B200RL_PS_NMAX; ++i) {
+    const double v = warp_max(m[i]);
+    if (lane == 0) partial_max[(size_t)blockIdx.x * B200RL_PS_NMAX + i] = v;
+  }
 }
 
 // (adv - mean) / (std + 1e-8), then optionally (adv - min) + 1e-8   (algos/util.py:7-12)
@@ -408,8 +483,13 @@ int b200rl_process_samples(int obs_dim, int N, int T, const float* obs, const fl
 #undef B200RL_PRED_LAUNCH
     B200RL_LAUNCH_CHECK("lfb_predict_kernel");
   }
-  gae_scan_kernel<<<grid, SC_THREADS, 0, st>>>(N, T, rew, base, flags, tstep, discount, discount * gae_lambda,
-                                               drop_cut_paths, adv, ret, psum, pmax);
+  const bool staged = (N % 32) == 0 && (((uintptr_t)rew | (uintptr_t)base | (uintptr_t)tstep | (uintptr_t)flags) & 15) == 0;
+  if (staged)
+    gae_scan_kernel<true><<<grid, SC_THREADS, 0, st>>>(N, T, rew, base, flags, tstep, discount, discount * gae_lambda,
+                                                       drop_cut_paths, adv, ret, psum, pmax);
+  else
+    gae_scan_kernel<false><<<grid, SC_THREADS, 0, st>>>(N, T, rew, base, flags, tstep, discount, discount * gae_lambda,
+                                                        drop_cut_paths, adv, ret, psum, pmax);
   B200RL_LAUNCH_CHECK("gae_scan_kernel");
   int rc = launch_finalize_sum(psum, grid, B200RL_PS_NSUM, sums_out, 1.0, st);
   if (rc) return rc;
