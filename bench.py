@@ -38,6 +38,9 @@ def make_env(name):
     if name == "cartpole_swingup":
         from rllab_b200.envs.box2d.cartpole_swingup_env import CartpoleSwingupEnv
         return normalize(CartpoleSwingupEnv())
+    if name == "double_pendulum":
+        from rllab_b200.envs.box2d.double_pendulum_env import DoublePendulumEnv
+        return normalize(DoublePendulumEnv())
     if name == "pendulum":
         from rllab_b200.envs.gym_env import GymEnv
         return normalize(GymEnv("Pendulum-v0"))

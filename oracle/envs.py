@@ -145,6 +145,62 @@ class CartPoleSwingupEnv(CartPoleEnv):
         return s2, r, done
 
 
+class DoublePendulumEnv(LaneEnv):
+    """Reduced-coordinate restatement of rllab/envs/box2d/double_pendulum_env.py:11-61 + box2d_env.py:119-183 +
+    models/double_pendulum.xml.mako [3P pybox2d: PARITY UNPINNED].
+
+    Two rods (compute_rect_vertices([0,0],[0,-link_len], 0.05): length L = link_len = 1, width 0.1, density 5 -> m = 0.5,
+    COM L/2 from the joint, I_com = m (w^2 + L^2)/12); link1 hinged to the static track at the origin, link2 to link1's
+    end; absolute body angles th1, th2 (CCW, 0 = hanging down: the rod points along (sin th, -cos th)); Box2D gravity
+    (0,-10) [3P default of the parser]; control type="torque" on link_joint_2, ctrllimit +-50: the revolute motor is
+    driven at +-1e5 with maxMotorTorque |u| (box2d_env.py:134-144), i.e. torque +u on link2 and -u on link1;
+    timestep 0.01, frame_skip 2 (:16), semi-implicit Euler (Box2D integrates v then x).
+      M(th) thdd = Q - C - dV:   M11 = I + m lc^2 + m L^2, M22 = I + m lc^2, M12 = m L lc cos(th1 - th2)
+      row 1: -u - m L lc sin(th1-th2) w2^2 - (m lc + m L) g sin th1      row 2: +u + m L lc sin(th1-th2) w1^2 - m g lc sin th2
+    reset (:31-41): th1, th2 ~ N(0, 0.1), w1, w2 ~ N(0, 0.01).  obs (state tags of the template): sin th1, cos th1, w1,
+    sin th2, cos th2, w2.  reward (post-step, :52-58) = -|tip - (0, 2L)| with get_tip_pos (:43-50) = link2.position -
+    L (sin th2, cos th2), link2.position = L (sin th1, -cos th1); never done (:60-61)."""
+    name, kind = "double_pendulum", 6
+    O, A, S, K = 6, 1, 4, 4
+    lb, ub = (-50.0,), (50.0,)
+    noise_kind = "normal"
+    L, m, lc, g, dt_, frame_skip = 1.0, 0.5, 0.5, 10.0, 0.01, 2
+    I = 0.5 * (0.1 ** 2 + 1.0 ** 2) / 12.0
+
+    def reset(self, raw):
+        dt = self.dtype
+        raw = np.asarray(raw, dt)
+        stds = np.asarray([0.1, 0.1, 0.01, 0.01], dt).reshape(4, 1)
+        return (stds * raw).astype(dt)                     # th1, th2, w1, w2
+
+    def obs(self, s):
+        return np.stack([np.sin(s[0]), np.cos(s[0]), s[2], np.sin(s[1]), np.cos(s[1]), s[3]]).astype(self.dtype)
+
+    def step(self, s, u):
+        dt = self.dtype
+        L, m, lc, g, I, h = (dt(v) for v in (self.L, self.m, self.lc, self.g, self.I, self.dt_))
+        th1, th2, w1, w2 = s[0], s[1], s[2], s[3]
+        tau = np.clip(u[0], dt(-50.0), dt(50.0))
+        m11, m22, mlc = I + m * lc * lc + m * L * L, I + m * lc * lc, m * L * lc
+        for _ in range(self.frame_skip):
+            sd, cd = np.sin(th1 - th2), np.cos(th1 - th2)
+            m12 = mlc * cd
+            b1 = -tau - mlc * sd * w2 * w2 - (m * lc + m * L) * g * np.sin(th1)
+            b2 = tau + mlc * sd * w1 * w1 - m * g * lc * np.sin(th2)
+            det = m11 * m22 - m12 * m12
+            a1 = (m22 * b1 - m12 * b2) / det
+            a2 = (m11 * b2 - m12 * b1) / det
+            w1 = w1 + h * a1
+            w2 = w2 + h * a2
+            th1 = th1 + h * w1
+            th2 = th2 + h * w2
+        s2 = np.stack([th1, th2, w1, w2]).astype(dt)
+        tx = L * np.sin(th1) - L * np.sin(th2)
+        ty = -L * np.cos(th1) - L * np.cos(th2)
+        r = -np.sqrt(tx * tx + (ty - dt(2.0) * L) ** 2)
+        return s2, r.astype(dt), np.zeros(r.shape, bool)
+
+
 class PendulumEnv(LaneEnv):
     """gym==0.7.4 Pendulum-v0 (`rllab/envs/gym_env.py:58-116` wraps it; environment.yml:52)
     [3P gym: PARITY UNPINNED].  max_speed 8, max_torque 2, dt .05, g 10, m 1, l 1.
@@ -188,6 +244,8 @@ def make(name, dtype=np.float64):
         return CartPoleEnv(dtype)
     if name in ("cartpole_swingup", "cartpoleswingupenv"):
         return CartPoleSwingupEnv(dtype)
+    if name in ("double_pendulum", "doublependulumenv"):
+        return DoublePendulumEnv(dtype)
     if name in ("pendulum", "pendulum-v0"):
         return PendulumEnv(dtype)
     if name in ("swimmer", "hopper"):

@@ -30,20 +30,22 @@ int num_sms() {
   return sms;
 }
 
-// out[k] = op over blocks of partial[b][k].  32 outputs x 8 block-slices per CTA: each slice walks every 8th block
-// (coalesced 256 B rows, 4 loads in flight), the slices are combined through shared memory in fixed order, so the result
-// is deterministic and the dependent-add chain is nblocks/8 long instead of nblocks (the one-thread-per-output version
-// cost ~56 us per call, 4 % of the cfg2 iteration -- profiles/r01c).
+// out[k] = op over blocks of partial[b][k].  32 outputs x FIN_SLICES block-slices per CTA: each slice walks every
+// FIN_SLICES-th block (coalesced 256 B rows, 4 loads in flight), the slices are combined through shared memory in fixed
+// order, so the result is deterministic and the dependent-add chain is nblocks/FIN_SLICES long instead of nblocks (the
+// one-thread-per-output version cost ~56 us per call -- profiles/r01c; 8 slices still 40 us on the 2 048 partials of
+// process_samples -- profiles/r02a).
+constexpr int FIN_SLICES = 32, FIN_THREADS = 32 * FIN_SLICES;
 template <bool IS_MAX>
-__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partial, int nblocks, int K,
+__global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(const double* __restrict__ partial, int nblocks, int K,
                                                        double* __restrict__ out, double scale) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[FIN_SLICES][33];
   const int kx = threadIdx.x & 31, by = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + kx;
   double acc = IS_MAX ? -1.0e300 : 0.0;
   if (k < K) {
 #pragma unroll 4
-    for (int b = by; b < nblocks; b += 8) {
+    for (int b = by; b < nblocks; b += FIN_SLICES) {
       const double v = partial[(size_t)b * K + k];
       acc = IS_MAX ? fmax(acc, v) : acc + v;
     }
@@ -53,19 +55,19 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
   if (by == 0 && k < K) {
     double r = sm[0][kx];
 #pragma unroll
-    for (int y = 1; y < 8; ++y) r = IS_MAX ? fmax(r, sm[y][kx]) : r + sm[y][kx];
+    for (int y = 1; y < FIN_SLICES; ++y) r = IS_MAX ? fmax(r, sm[y][kx]) : r + sm[y][kx];
     out[k] = IS_MAX ? r : r * scale;
   }
 }
 
 int launch_finalize_sum(const double* partial, int nblocks, int K, double* out, double scale, cudaStream_t s) {
-  finalize_kernel<false><<<(K + 31) / 32, 256, 0, s>>>(partial, nblocks, K, out, scale);
+  finalize_kernel<false><<<(K + 31) / 32, FIN_THREADS, 0, s>>>(partial, nblocks, K, out, scale);
   B200RL_LAUNCH_CHECK("finalize_kernel<sum>");
   return 0;
 }
 
 int launch_finalize_max(const double* partial, int nblocks, int K, double* out, cudaStream_t s) {
-  finalize_kernel<true><<<(K + 31) / 32, 256, 0, s>>>(partial, nblocks, K, out, 1.0);
+  finalize_kernel<true><<<(K + 31) / 32, FIN_THREADS, 0, s>>>(partial, nblocks, K, out, 1.0);
   B200RL_LAUNCH_CHECK("finalize_kernel<max>");
   return 0;
 }
@@ -74,8 +76,8 @@ int launch_finalize_max(const double* partial, int nblocks, int K, double* out, 
 // communicator (f.peer.world > 1) every block pushes its outputs into slot[rank] of all exchange windows instead of
 // writing them out, the last block to finish signals the peers, and every block then folds the `world` slots of the own
 // window in rank order (peer.cuh) -- the reduction over blocks and the all-reduce over GPUs are one launch.
-__global__ void __launch_bounds__(256) finalize_update_kernel(FinArgs f) {
-  __shared__ double sm[8][33];
+__global__ void __launch_bounds__(FIN_THREADS) finalize_update_kernel(FinArgs f) {
+  __shared__ double sm[FIN_SLICES][33];
   __shared__ int sh_last, sh_ok;
   const int kx = threadIdx.x & 31, by = threadIdx.x >> 5;
   const double sc = f.scale / (f.count != nullptr ? f.count[0] : 1.0);
@@ -92,14 +94,14 @@ __global__ void __launch_bounds__(256) finalize_update_kernel(FinArgs f) {
     double acc = 0.0;
     if (k < f.K) {
 #pragma unroll 4
-      for (int b = by; b < f.nblocks; b += 8) acc += f.partial[(size_t)b * f.K + k];
+      for (int b = by; b < f.nblocks; b += FIN_SLICES) acc += f.partial[(size_t)b * f.K + k];
     }
     sm[by][kx] = acc;
     __syncthreads();
     if (by == 0 && k < f.K) {
       r = sm[0][kx];
 #pragma unroll
-      for (int y = 1; y < 8; ++y) r += sm[y][kx];
+      for (int y = 1; y < FIN_SLICES; ++y) r += sm[y][kx];
       r *= sc;
       const bool is_ls = (k >= f.ols && k < f.ols + f.A);
       if (f.post == FIN_GRAD) {
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(256) finalize_update_kernel(FinArgs f) {
     // tuple: entries [0, NT-1) are sums, entry NT-1 is a max; thread (by, kx): kx < NT handles column kx
     double acc = (kx == f.NT - 1) ? -1.0e300 : 0.0;
     if (kx < f.NT) {
-      for (int b = by; b < f.nblocks; b += 8) {
+      for (int b = by; b < f.nblocks; b += FIN_SLICES) {
         const double v = f.tri_partial[(size_t)b * f.NT + kx];
         acc = (kx == f.NT - 1) ? fmax(acc, v) : acc + v;
       }
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(256) finalize_update_kernel(FinArgs f) {
       r = sm[0][kx];
       is_max = (kx == f.NT - 1);
 #pragma unroll
-      for (int y = 1; y < 8; ++y) r = is_max ? fmax(r, sm[y][kx]) : r + sm[y][kx];
+      for (int y = 1; y < FIN_SLICES; ++y) r = is_max ? fmax(r, sm[y][kx]) : r + sm[y][kx];
       if (!is_max) r *= sc;
       slot_i = f.K + kx;
       if (!peered) f.tri_out[kx] = r;
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(256) finalize_update_kernel(FinArgs f) {
 
 int launch_finalize_update(const FinArgs& f, cudaStream_t s) {
   const int nvb = (f.K + 31) / 32;
-  finalize_update_kernel<<<nvb + (f.tri_out != nullptr ? 1 : 0), 256, 0, s>>>(f);
+  finalize_update_kernel<<<nvb + (f.tri_out != nullptr ? 1 : 0), FIN_THREADS, 0, s>>>(f);
   B200RL_LAUNCH_CHECK("finalize_update_kernel");
   return 0;
 }

@@ -102,6 +102,61 @@ struct CartPoleSwingupEnvD {
   }
 };
 
+// ---------------------------------------------------------------- rllab/envs/box2d/double_pendulum_env.py:11-61
+// Reduced-coordinate restatement of models/double_pendulum.xml.mako (see oracle/envs.py::DoublePendulumEnv): two rods of
+// length L = 1 (width 0.1, density 5 -> m = 0.5, I_com = m (w^2 + L^2) / 12) hanging from the origin, absolute body angles
+// th1, th2 (CCW, 0 = hanging down), gravity (0, -10), torque u in [-50, 50] on the joint between the links (+u on link 2,
+// -u on link 1: the revolute motor of box2d_env.py:134-144), semi-implicit Euler, dt = 0.01, frame_skip = 2.
+// obs = [sin th1, cos th1, w1, sin th2, cos th2, w2]; reward (post-step) = -|tip - (0, 2L)| with the reference's tip
+// formula (double_pendulum_env.py:43-50: link-2 origin minus L (sin th2, cos th2)); never done.
+struct DoublePendulumEnvD {
+  static constexpr int KIND = B200RL_ENV_DOUBLE_PENDULUM, O = 6, A = 1, S = 4, K = 4, NOISE = B200RL_NOISE_NORMAL;
+  __host__ __device__ static constexpr float lb(int) { return -50.0f; }
+  __host__ __device__ static constexpr float ub(int) { return 50.0f; }
+  __device__ static void reset(float (&s)[S], const float (&raw)[K]) {
+    s[0] = 0.1f * raw[0]; s[1] = 0.1f * raw[1]; s[2] = 0.01f * raw[2]; s[3] = 0.01f * raw[3];   // th1, th2, w1, w2
+  }
+  __device__ static void obs(const float (&s)[S], float (&o)[O]) {
+    float sn, cs;
+    sincosf(s[0], &sn, &cs);
+    o[0] = sn; o[1] = cs; o[2] = s[2];
+    sincosf(s[1], &sn, &cs);
+    o[3] = sn; o[4] = cs; o[5] = s[3];
+  }
+  __device__ static void step(float (&s)[S], const float (&u)[A], float& r, bool& done) {
+    const float L = 1.0f, m = 0.5f, lc = 0.5f, g = 10.0f, h = 0.01f;
+    const float I = 0.5f * (0.1f * 0.1f + 1.0f) / 12.0f;
+    const float m11 = I + m * lc * lc + m * L * L, m22 = I + m * lc * lc, mlc = m * L * lc;
+    float th1 = s[0], th2 = s[1], w1 = s[2], w2 = s[3];
+    const float tau = fminf(fmaxf(u[0], -50.0f), 50.0f);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {                 // frame_skip = 2 (double_pendulum_env.py:16)
+      float sd, cd, s1, c1, s2, c2;
+      sincosf(th1 - th2, &sd, &cd);
+      sincosf(th1, &s1, &c1);
+      sincosf(th2, &s2, &c2);
+      const float m12 = mlc * cd;
+      const float b1 = -tau - mlc * sd * w2 * w2 - (m * lc + m * L) * g * s1;
+      const float b2 = tau + mlc * sd * w1 * w1 - m * g * lc * s2;
+      const float idet = 1.0f / (m11 * m22 - m12 * m12);
+      const float a1 = (m22 * b1 - m12 * b2) * idet;
+      const float a2 = (m11 * b2 - m12 * b1) * idet;
+      w1 += h * a1;
+      w2 += h * a2;
+      th1 += h * w1;
+      th2 += h * w2;
+    }
+    s[0] = th1; s[1] = th2; s[2] = w1; s[3] = w2;
+    float s1, c1, s2, c2;
+    sincosf(th1, &s1, &c1);
+    sincosf(th2, &s2, &c2);
+    const float tx = L * s1 - L * s2, ty = -L * c1 - L * c2;      // link-2 origin (L sin th1, -L cos th1) - L (sin th2, cos th2)
+    const float dx = tx, dy = ty - 2.0f * L;
+    r = -sqrtf(dx * dx + dy * dy);
+    done = false;
+  }
+};
+
 // ---------------------------------------------------------------- gym 0.7.4 Pendulum-v0 via rllab/envs/gym_env.py:58-116
 struct PendulumEnvD {
   static constexpr int KIND = B200RL_ENV_PENDULUM, O = 3, A = 1, S = 2, K = 2, NOISE = B200RL_NOISE_UNIFORM;
@@ -154,6 +209,7 @@ namespace b200rl {
     case B200RL_ENV_CARTPOLE: { using Env = ::b200rl::CartPoleEnvD; __VA_ARGS__; } break;     \
     case B200RL_ENV_PENDULUM: { using Env = ::b200rl::PendulumEnvD; __VA_ARGS__; } break;     \
     case B200RL_ENV_CARTPOLE_SWINGUP: { using Env = ::b200rl::CartPoleSwingupEnvD; __VA_ARGS__; } break; \
+    case B200RL_ENV_DOUBLE_PENDULUM: { using Env = ::b200rl::DoublePendulumEnvD; __VA_ARGS__; } break; \
     B200RL_PLANAR_CASES(__VA_ARGS__)                                                          \
     default:                                                                                  \
       ::b200rl::set_error("unknown env kind %d", (int)(kind));                                \

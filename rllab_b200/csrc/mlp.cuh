@@ -147,7 +147,7 @@ __device__ __forceinline__ void mlp_forward_thread(const float* __restrict__ sp,
 // log_std after the min_std clamp (gaussian_mlp_policy.py:100-101): max(param, log(min_std))
 __device__ __forceinline__ float clamp_log_std(float param, float log_min_std) { return fmaxf(param, log_min_std); }
 
-// Supported network shapes: (O, A) of the five env kinds x hidden (32,32) | (64,64).
+// Supported network shapes: (O, A) of the compiled env kinds x hidden (32,32) | (64,64).
 #define B200RL_DISPATCH_NET_OA(O_, A_, H_, ...)                                             \
   if (obs_dim == O_ && act_dim == A_ && h1 == H_ && h2 == H_) {                              \
     using NetT = ::b200rl::Net<O_, H_, H_, A_>;                                              \
@@ -158,6 +158,7 @@ __device__ __forceinline__ float clamp_log_std(float param, float log_min_std) {
   B200RL_DISPATCH_NET_OA(2, 2, H_, __VA_ARGS__)                                              \
   B200RL_DISPATCH_NET_OA(4, 1, H_, __VA_ARGS__)                                              \
   B200RL_DISPATCH_NET_OA(3, 1, H_, __VA_ARGS__)                                              \
+  B200RL_DISPATCH_NET_OA(6, 1, H_, __VA_ARGS__)                                              \
   B200RL_DISPATCH_NET_OA(13, 2, H_, __VA_ARGS__)                                             \
   B200RL_DISPATCH_NET_OA(20, 3, H_, __VA_ARGS__)                                             \
   {                                                                                          \
@@ -169,11 +170,13 @@ __device__ __forceinline__ float clamp_log_std(float param, float log_min_std) {
   B200RL_DISPATCH_NET_OA(2, 2, 32, __VA_ARGS__)                                              \
   B200RL_DISPATCH_NET_OA(4, 1, 32, __VA_ARGS__)                                              \
   B200RL_DISPATCH_NET_OA(3, 1, 32, __VA_ARGS__)                                              \
+  B200RL_DISPATCH_NET_OA(6, 1, 32, __VA_ARGS__)                                              \
   B200RL_DISPATCH_NET_OA(13, 2, 32, __VA_ARGS__)                                             \
   B200RL_DISPATCH_NET_OA(20, 3, 32, __VA_ARGS__)                                             \
   B200RL_DISPATCH_NET_OA(2, 2, 64, __VA_ARGS__)                                              \
   B200RL_DISPATCH_NET_OA(4, 1, 64, __VA_ARGS__)                                              \
   B200RL_DISPATCH_NET_OA(3, 1, 64, __VA_ARGS__)                                              \
+  B200RL_DISPATCH_NET_OA(6, 1, 64, __VA_ARGS__)                                              \
   B200RL_DISPATCH_NET_OA(13, 2, 64, __VA_ARGS__)                                             \
   B200RL_DISPATCH_NET_OA(20, 3, 64, __VA_ARGS__)                                             \
   {                                                                                          \
@@ -183,7 +186,7 @@ __device__ __forceinline__ float clamp_log_std(float param, float log_min_std) {
 
 inline bool net_supported(int O, int h1, int h2, int A) {
   if (h1 != h2 || (h1 != 32 && h1 != 64)) return false;
-  return (O == 2 && A == 2) || (O == 4 && A == 1) || (O == 3 && A == 1) || (O == 13 && A == 2) || (O == 20 && A == 3);
+  return (O == 2 && A == 2) || (O == 4 && A == 1) || (O == 3 && A == 1) || (O == 6 && A == 1) || (O == 13 && A == 2) || (O == 20 && A == 3);
 }
 
 }  // namespace b200rl

@@ -125,13 +125,25 @@ int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, 
   cudaStream_t st = (cudaStream_t)stream;
   UpdArgs a{};
   fill_args(a, params_f32, min_std, B, obs, act, adv, old_mean, old_log_std, loss_kind, flags, ws);
-  long long g = (long long)num_sms() * 4;
-  const long long need = (B + LOSS_THREADS - 1) / LOSS_THREADS;
-  if (g > need) g = need;
-  if (g > MAX_PARTIAL_BLOCKS) g = MAX_PARTIAL_BLOCKS;
-  const int grid = (int)g;
-  B200RL_DISPATCH_NET({ loss_thread_kernel<NetT><<<grid, LOSS_THREADS, 0, st>>>(a); });
-  B200RL_LAUNCH_CHECK("loss_thread_kernel");
+  int grid = 0;
+#ifndef B200RL_AB_TILE32
+  if (h1 == 32 && h2 == 32) {
+    // 32-wide nets: forward-only mode of the tcgen05 kernel (update_umma32.cu) -- the same forward, instruction for
+    // instruction, as the gradient pass, so (loss, KL) of the two passes agree bit for bit at equal theta
+    int P = 0, ols = 0;
+    int rc = update_umma32_launch(MODE_LOSS, obs_dim, act_dim, a, &grid, &P, &ols, st);
+    if (rc) return rc;
+  } else
+#endif
+  {
+    long long g = (long long)num_sms() * 4;
+    const long long need = (B + LOSS_THREADS - 1) / LOSS_THREADS;
+    if (g > need) g = need;
+    if (g > MAX_PARTIAL_BLOCKS) g = MAX_PARTIAL_BLOCKS;
+    grid = (int)g;
+    B200RL_DISPATCH_NET({ loss_thread_kernel<NetT><<<grid, LOSS_THREADS, 0, st>>>(a); });
+    B200RL_LAUNCH_CHECK("loss_thread_kernel");
+  }
   FinArgs f{};
   f.partial = nullptr; f.nblocks = grid; f.K = 0; f.vec_out = nullptr;
   f.tri_partial = ws; f.NT = 3; f.tri_out = out; f.scale = scale; f.count = count; f.post = FIN_NONE;

@@ -103,14 +103,35 @@ static int launch_tile(const UpdArgs& a, int* grid_out, cudaStream_t st) {
   return 0;
 }
 
+// The shipped library reaches this FP32 formulation only for the Fisher-vector product without an activation cache (the
+// tcgen05 kernels serve b200rl_grad); its gradient instantiations are built for the A/B variant only
+// (-DB200RL_AB_TILE32, README.md).
+namespace {   // per translation unit: update_tile.cu and update_gemm.cu each have their own
+#ifdef B200RL_AB_TILE32
+constexpr bool kFfmaGradBuilt = true;
+#else
+constexpr bool kFfmaGradBuilt = false;
+#endif
+template <class N, bool BUILT>
+struct FfmaGrad {
+  static int run(const UpdArgs& a, int* grid_out, cudaStream_t st) { return launch_tile<N, MODE_GRAD>(a, grid_out, st); }
+};
+template <class N>
+struct FfmaGrad<N, false> {
+  static int run(const UpdArgs&, int*, cudaStream_t) {
+    set_error("the FP32 gradient kernels are not part of this build (the tcgen05 kernels serve b200rl_grad)");
+    return B200RL_EUNSUPPORTED;
+  }
+};
+}  // namespace
+
 int update_tile_launch(int mode, int obs_dim, int act_dim, const UpdArgs& a, int* grid_out, int* P_out, int* ols_out,
                        cudaStream_t st) {
   const int h1 = 32, h2 = 32;
   B200RL_DISPATCH_NET_H(32, {
     *P_out = NetT::P;
     *ols_out = NetT::ols;
-    int rc = (mode == MODE_GRAD) ? launch_tile<NetT, MODE_GRAD>(a, grid_out, st)
-                                 : launch_tile<NetT, MODE_FVP>(a, grid_out, st);
+    int rc = (mode == MODE_GRAD) ? FfmaGrad<NetT, kFfmaGradBuilt>::run(a, grid_out, st) : launch_tile<NetT, MODE_FVP>(a, grid_out, st);
     if (rc) return rc;
   });
   return 0;

@@ -48,29 +48,31 @@ struct Umma32 {
   static constexpr int KX = ((O + 7) / 8) * 8;                 // obs columns of the X operand, zero padded
   // TMEM columns (float32 each): accumulators (the gradient pass uses them strictly one after the other: one slot), X
   // hi/lo, one A-operand slot (H1, then T1 / D2) hi/lo
-  static constexpr int cACC_A = 0, cACC_B = (MODE == MODE_GRAD) ? 0 : 32, cX_HI = cACC_B + 32, cX_LO = cX_HI + KX,
+  static constexpr int cACC_A = 0, cACC_B = (MODE == MODE_FVP) ? 32 : 0, cX_HI = cACC_B + 32, cX_LO = cX_HI + KX,
                        cOP_HI = cX_LO + KX, cOP_LO = cOP_HI + 32, cEND = cOP_LO + 32;
   static constexpr int TMEM_COLS = cEND <= 128 ? 128 : 256;
   static constexpr int IMG = 32 * 32 * 4, IMGX = 32 * KX * 4;   // bytes of one [32 x K] operand image
   // weight images (hi then lo).  GRAD: W0^T [j][o], W1^T [j][i], W1 [i][j].  FVP: V0^T, V1^T, W1^T, W1.
+  // LOSS (forward only): W0^T, W1^T.
   static constexpr int o_bXT = 0, o_bW1T = o_bXT + 2 * IMGX, o_bW1 = o_bW1T + 2 * IMG,
-                       o_bV1T = o_bW1 + 2 * IMG, o_img_end = o_bV1T + (MODE == MODE_FVP ? 2 * IMG : 0);
+                       o_bV1T = o_bW1 + (MODE == MODE_LOSS ? 0 : 2 * IMG),
+                       o_img_end = o_bV1T + (MODE == MODE_FVP ? 2 * IMG : 0);
   // small parameters (floats): GRAD b0[32] b1[32] Wout[32A] bout[A];  FVP vb0[32] vb1[32] Wout[32A] Vout[32A] vbout[A]
   static constexpr int n_small = ((64 + 2 * H * A + A + 3) / 4) * 4;
   static constexpr int o_small = o_img_end, o_stage = o_small + n_small * 4;
   // stage rows; D1 reuses the H2 rows (H2 is dead once part A of the Gram phase has run, D1 only exists after it)
+  // (the forward-only loss pass stages nothing)
   static constexpr int rX = 0, rH1 = rX + O, rH2 = rH1 + H, rD1 = rH2, rD2 = rH2 + H, rDM = rD2 + H, rDL = rDM + A,
-                       R = rDL + A;
+                       R = (MODE == MODE_LOSS) ? 0 : rDL + A;
   static constexpr int o_red = ((o_stage + R * V_LD * 4 + 15) / 16) * 16;   // 3 x 32 doubles of reduction scratch
   static constexpr int o_bar = o_red + 3 * 32 * 8;
   static constexpr size_t bytes = (size_t)o_bar + 64;
-  static_assert(2 * 64 * 16 * 8 <= R * V_LD * 4, "stage region must hold the K-half combine scratch");
+  static_assert(MODE == MODE_LOSS || 2 * 64 * 16 * 8 <= R * V_LD * 4, "stage region must hold the K-half combine scratch");
   static_assert(bytes <= 232448, "does not fit the 227 KB of shared memory");
   // resident CTAs per SM: shared memory (228 KB, 1 KB reserved per CTA), TMEM (512 columns), registers (64 K / 128 threads)
   static constexpr int by_smem = (int)((228 * 1024) / (bytes + 1024)), by_tmem = 512 / TMEM_COLS;
-  static constexpr int MINB = (by_smem < by_tmem ? by_smem : by_tmem) < B200RL_V_MAXB
-                                  ? ((by_smem < by_tmem ? by_smem : by_tmem) < 1 ? 1 : (by_smem < by_tmem ? by_smem : by_tmem))
-                                  : B200RL_V_MAXB;
+  static constexpr int cap = (MODE == MODE_LOSS) ? 4 : B200RL_V_MAXB, by_res = by_smem < by_tmem ? by_smem : by_tmem;
+  static constexpr int MINB = by_res < cap ? (by_res < 1 ? 1 : by_res) : cap;
 };
 
 // element (n, k) of a K-major [32 x K] image, byte offset
@@ -104,8 +106,10 @@ __global__ void __launch_bounds__(V_THREADS, (Umma32<N, MODE>::MINB)) update_umm
     const float wh = tf32_hi(w);
     *reinterpret_cast<float*>(smem + SM::o_bW1T + v_boff(j, i)) = wh;
     *reinterpret_cast<float*>(smem + SM::o_bW1T + SM::IMG + v_boff(j, i)) = w - wh;
-    *reinterpret_cast<float*>(smem + SM::o_bW1 + v_boff(i, j)) = wh;
-    *reinterpret_cast<float*>(smem + SM::o_bW1 + SM::IMG + v_boff(i, j)) = w - wh;
+    if constexpr (MODE != MODE_LOSS) {
+      *reinterpret_cast<float*>(smem + SM::o_bW1 + v_boff(i, j)) = wh;
+      *reinterpret_cast<float*>(smem + SM::o_bW1 + SM::IMG + v_boff(i, j)) = w - wh;
+    }
     if constexpr (MODE == MODE_FVP) {
       const float v = (float)a.xvec[N::oW1 + e];
       const float vh = tf32_hi(v);
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(V_THREADS, (Umma32<N, MODE>::MINB)) update_umm
   };
 
   TileGram<N, SM::rX, SM::rH1, SM::rH2, SM::rD1, SM::rD2, SM::rDM, LD, B200RL_V_PACKED_GRAM != 0> gram;
-  gram.init();
+  if constexpr (MODE != MODE_LOSS) gram.init();
   double s_loss = 0.0, s_kl = 0.0, m_kl = -1.0e300;
   bool timed_out = false;
 
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(V_THREADS, (Umma32<N, MODE>::MINB)) update_umm
         float x = 0.f;
         if (o < O) {
           x = a.obs[(size_t)o * a.B + sl];
-          colX[o * LD] = x;
+          if constexpr (MODE != MODE_LOSS) colX[o * LD] = x;
         }
         const float xh = tf32_hi(x);
         hi[o] = __float_as_uint(xh);
@@ -242,9 +246,9 @@ __global__ void __launch_bounds__(V_THREADS, (Umma32<N, MODE>::MINB)) update_umm
         split_gemm(SM::cACC_B, SM::cOP_HI, SM::cOP_LO, dV1T_hi, dV1T_lo, 4, false);            // H1 V1
       u_commit(&bars[0]);
     }
-    // GRAD: the remaining per-sample inputs, requested while the first GEMM runs
+    // GRAD / LOSS: the remaining per-sample inputs, requested while the first GEMM runs
     float act[A], om[A], adv_s = 0.f;
-    if constexpr (MODE == MODE_GRAD) {
+    if constexpr (MODE != MODE_FVP) {
 #pragma unroll
       for (int k = 0; k < A; ++k) {
         act[k] = a.act[(size_t)k * a.B + sl];
@@ -259,14 +263,14 @@ __global__ void __launch_bounds__(V_THREADS, (Umma32<N, MODE>::MINB)) update_umm
       uint32_t r[32];
       u_ld32(tlane + SM::cACC_A, r);
       float v[32];
-      if constexpr (MODE == MODE_GRAD) {
+      if constexpr (MODE != MODE_FVP) {
 #pragma unroll
         for (int c = 0; c < H; ++c) {
           h1[c] = tanh_f(__uint_as_float(r[c]) + sb0[c]);
-          colH1[c * LD] = h1[c];
+          if constexpr (MODE == MODE_GRAD) colH1[c * LD] = h1[c];
           v[c] = h1[c];
         }
-        if (a.h_cache != nullptr && inrange) {
+        if (MODE == MODE_GRAD && a.h_cache != nullptr && inrange) {
 #pragma unroll
           for (int c = 0; c < H; ++c) a.h_cache[(size_t)c * a.B + sl] = h1[c];
         }
@@ -290,13 +294,13 @@ __global__ void __launch_bounds__(V_THREADS, (Umma32<N, MODE>::MINB)) update_umm
       uint32_t r[32];
       u_ld32(tlane + SM::cACC_B, r);
       float dmu[A];
-      if constexpr (MODE == MODE_GRAD) {
+      if constexpr (MODE != MODE_FVP) {
 #pragma unroll
         for (int c = 0; c < H; ++c) {
           h2[c] = tanh_f(__uint_as_float(r[c]) + sb1[c]);
-          colH2[c * LD] = h2[c];
+          if constexpr (MODE == MODE_GRAD) colH2[c * LD] = h2[c];
         }
-        if (a.h_cache != nullptr && inrange) {
+        if (MODE == MODE_GRAD && a.h_cache != nullptr && inrange) {
 #pragma unroll
           for (int c = 0; c < H; ++c) a.h_cache[(size_t)(H + c) * a.B + sl] = h2[c];
         }
@@ -330,11 +334,13 @@ __global__ void __launch_bounds__(V_THREADS, (Umma32<N, MODE>::MINB)) update_umm
         if (!valid) { w_s = 0.f; term = 0.f; }
         s_loss += (double)term;
         if (valid) { s_kl += (double)kl; m_kl = fmax(m_kl, (double)kl); }
+        if constexpr (MODE == MODE_GRAD) {
 #pragma unroll
-        for (int k = 0; k < A; ++k) {
-          dmu[k] = -w_s * z[k] * D.inv_std[k];
-          colDM[k * LD] = dmu[k];
-          colDL[k * LD] = -w_s * (z[k] * z[k] - 1.0f);
+          for (int k = 0; k < A; ++k) {
+            dmu[k] = -w_s * z[k] * D.inv_std[k];
+            colDM[k * LD] = dmu[k];
+            colDL[k * LD] = -w_s * (z[k] * z[k] - 1.0f);
+          }
         }
       } else {
         float md[A];
@@ -354,51 +360,60 @@ __global__ void __launch_bounds__(V_THREADS, (Umma32<N, MODE>::MINB)) update_umm
           colDL[k * LD] = 0.f;
         }
       }
-      float v[32];
+      if constexpr (MODE != MODE_LOSS) {
+        float v[32];
 #pragma unroll
-      for (int c = 0; c < H; ++c) {
-        float sacc = 0.f;
+        for (int c = 0; c < H; ++c) {
+          float sacc = 0.f;
 #pragma unroll
-        for (int k = 0; k < A; ++k) sacc = fmaf(dmu[k], sWout[c * A + k], sacc);
-        v[c] = sacc * (1.0f - h2[c] * h2[c]);
-        colD2[c * LD] = v[c];
+          for (int k = 0; k < A; ++k) sacc = fmaf(dmu[k], sWout[c * A + k], sacc);
+          v[c] = sacc * (1.0f - h2[c] * h2[c]);
+          colD2[c * LD] = v[c];
+        }
+        put_operand(v);
       }
-      put_operand(v);
     }
-    u_fence_before();
-    __syncthreads();
-    if (tid == 0) {
+    if constexpr (MODE != MODE_LOSS) {
+      u_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        u_fence_after();
+        split_gemm(SM::cACC_A, SM::cOP_HI, SM::cOP_LO, dW1_hi, dW1_lo, 4, false);               // D2 W1^T
+        u_commit(&bars[2]);
+      }
+      // ================= Gram part A behind the last GEMM: dW1 = H1^T D2, dWout, db1, dbout, dlog_std (tile_gram.cuh)
+      gram.accumulate_a(stage, tid);
+      __syncthreads();                       // every thread is done with the H2 rows: D1 may overwrite them
+      timed_out |= !u_wait(&bars[2], phase);
       u_fence_after();
-      split_gemm(SM::cACC_A, SM::cOP_HI, SM::cOP_LO, dW1_hi, dW1_lo, 4, false);                 // D2 W1^T
-      u_commit(&bars[2]);
-    }
-    // ================= Gram part A behind the last GEMM: dW1 = H1^T D2, dWout, db1, dbout, dlog_std (tile_gram.cuh)
-    gram.accumulate_a(stage, tid);
-    __syncthreads();                       // every thread is done with the H2 rows: D1 may overwrite them
-    timed_out |= !u_wait(&bars[2], phase);
-    u_fence_after();
-    // ================= E3 / G: d1 = D1pre (1 - h1^2)
-    {
-      uint32_t r[32];
-      u_ld32(tlane + SM::cACC_A, r);
+      // ================= E3 / G: d1 = D1pre (1 - h1^2)
+      {
+        uint32_t r[32];
+        u_ld32(tlane + SM::cACC_A, r);
 #pragma unroll
-      for (int c = 0; c < H; ++c) colD1[c * LD] = __uint_as_float(r[c]) * (1.0f - h1[c] * h1[c]);
+        for (int c = 0; c < H; ++c) colD1[c * LD] = __uint_as_float(r[c]) * (1.0f - h1[c] * h1[c]);
+      }
+      u_fence_before();
+      __syncthreads();
+      // ================= Gram part B: dW0 = X^T D1, db0
+      gram.accumulate_b(stage, tid);
+      __syncthreads();
     }
-    u_fence_before();
-    __syncthreads();
-    // ================= Gram part B: dW0 = X^T D1, db0
-    gram.accumulate_b(stage, tid);
-    __syncthreads();
   }
 
-  double* out = a.partial + (size_t)blockIdx.x * P;
-  gram.write(out, reinterpret_cast<double*>(stage), tid);
-  __syncthreads();
-  if (timed_out) out[tid % P] = __longlong_as_double(0x7FF8000000000000ll);   // an MMA never completed: poison the result
-  if constexpr (MODE == MODE_GRAD) {
+  if constexpr (MODE != MODE_LOSS) {
+    double* out = a.partial + (size_t)blockIdx.x * P;
+    gram.write(out, reinterpret_cast<double*>(stage), tid);
+    __syncthreads();
+    if (timed_out) out[tid % P] = __longlong_as_double(0x7FF8000000000000ll);   // an MMA never completed: poison the result
+  } else if (timed_out) {
+    s_loss = __longlong_as_double(0x7FF8000000000000ll);
+  }
+  if constexpr (MODE != MODE_FVP) {
+    // per-block (loss, sum KL | max KL): after the [grid][P] partial vectors (GRAD) or alone (LOSS), as loss_thread_kernel
     double v[2] = {s_loss, s_kl};
     double mx[1] = {m_kl};
-    double* sc = a.partial + (size_t)gridDim.x * P + (size_t)blockIdx.x * 3;
+    double* sc = a.partial + (MODE == MODE_GRAD ? (size_t)gridDim.x * P : (size_t)0) + (size_t)blockIdx.x * 3;
     block_reduce_store<2, false>(v, red_scratch, sc);
     block_reduce_store<1, true>(mx, red_scratch, sc + 2);
   }
@@ -428,8 +443,9 @@ int update_umma32_launch(int mode, int obs_dim, int act_dim, const UpdArgs& a, i
   B200RL_DISPATCH_NET_H(32, {
     *P_out = NetT::P;
     *ols_out = NetT::ols;
-    int rc = (mode == MODE_GRAD) ? launch_umma32<NetT, MODE_GRAD>(a, grid_out, st)
-                                 : launch_umma32<NetT, MODE_FVP>(a, grid_out, st);
+    int rc = (mode == MODE_GRAD)   ? launch_umma32<NetT, MODE_GRAD>(a, grid_out, st)
+             : (mode == MODE_LOSS) ? launch_umma32<NetT, MODE_LOSS>(a, grid_out, st)
+                                   : launch_umma32<NetT, MODE_FVP>(a, grid_out, st);
     if (rc) return rc;
   });
   return 0;

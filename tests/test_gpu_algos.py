@@ -190,7 +190,7 @@ def test_samples_data_wire_format(dev):
     np.testing.assert_allclose(p0["returns"], S.discount_cumsum(p0["rewards"], 0.99), rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("env_name", ["point", "cartpole", "pendulum", "cartpole_swingup", "swimmer", "hopper"])
+@pytest.mark.parametrize("env_name", ["point", "cartpole", "pendulum", "cartpole_swingup", "double_pendulum", "swimmer", "hopper"])
 def test_env_protocol(dev, env_name):
     """tests/envs/test_envs.py:86-102: reset in obs space, action in action space, one step, scalar reward."""
     env = _make(env_name)

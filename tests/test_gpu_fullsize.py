@@ -70,18 +70,21 @@ def test_returns_and_advantages_satisfy_their_recurrences(full):
     assert abs(float(a.mean())) < 1e-6 and abs(float(a.std(unbiased=False)) - 1.0) < 1e-5
 
 
-def test_loss_and_kl_are_exact_at_theta_old(full):
+def test_loss_and_kl_at_theta_old(full):
+    """At theta_old the surrogate is -mean(adv) and the KL is 0.  The 32-wide update passes run their forward on the
+    tensor cores (3xTF32 split, update_umma32.cu), so this holds to float32 rounding of the mean (1e-7), not bit for bit as
+    with the FFMA kernels of round 1; the loss pass and the gradient pass share one forward and agree with each other
+    far below that."""
     L, ops, b, th32 = full["L"], full["ops"], full["b"], full["th32"]
     out = torch.zeros(3, dtype=torch.float64, device=full["dev"])
     ops.loss_kl(L.LOSS_TRPO, th32, (4, H, H, 1), 1e-6, b, out)
     o = out.cpu().numpy()
-    assert abs(o[0] + float(b.adv.double().mean())) < 1e-12 and o[1] == 0.0 and o[2] == 0.0
+    assert abs(o[0] + float(b.adv.double().mean())) < 1e-6 and abs(o[1]) < 1e-10 and abs(o[2]) < 1e-8
     g = torch.zeros(full["dims"].P, dtype=torch.float64, device=full["dev"])
     out2 = torch.zeros(3, dtype=torch.float64, device=full["dev"])
-    # the gradient pass runs its forward on the tensor cores (3xTF32, update_umma32.cu): the same mean to ~1e-7, not bit
-    # for bit, so its triple is -mean(adv) / 0 to float32 rounding rather than exactly
     ops.grad(L.LOSS_TRPO, th32, (4, H, H, 1), 1e-6, b, g, out2)
-    assert abs(float(out2[0]) - o[0]) < 1e-6 and abs(float(out2[1])) < 1e-10 and abs(float(out2[2])) < 1e-8
+    o2 = out2.cpu().numpy()
+    assert abs(o2[0] - o[0]) < 1e-9 and abs(o2[1] - o[1]) < 1e-13 and abs(o2[2] - o[2]) < 1e-11, (o, o2)
 
 
 def test_fvp_is_linear_symmetric_and_positive(full):

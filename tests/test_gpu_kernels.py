@@ -33,7 +33,7 @@ def _L():
     return _lib
 
 
-ENVS = ["point", "cartpole", "pendulum", "cartpole_swingup"]
+ENVS = ["point", "cartpole", "pendulum", "cartpole_swingup", "double_pendulum"]
 try:
     from oracle import planar as _planar      # noqa: F401
     ENVS += ["swimmer", "hopper"]
@@ -365,7 +365,7 @@ def _update_setup(dev, env_name, hidden, N=512, T=32):
     return ops, env, dims, theta, b, batch
 
 
-@pytest.mark.parametrize("env_name,hidden", [("cartpole", 32), ("point", 32), ("pendulum", 32), ("cartpole", 64)] +
+@pytest.mark.parametrize("env_name,hidden", [("cartpole", 32), ("point", 32), ("pendulum", 32), ("double_pendulum", 32), ("cartpole", 64)] +
                          ([("swimmer", 32), ("hopper", 64)] if "hopper" in ENVS else []))
 def test_loss_kl_grad_fvp_match_oracle(dev, env_name, hidden):
     _check_update_kernels(dev, env_name, hidden, 512, 32)
@@ -385,10 +385,14 @@ def _check_update_kernels(dev, env_name, hidden, N, T):
     B = b.B
     th32 = torch.tensor(theta, dtype=torch.float32, device=dev)
     out = torch.zeros(3, dtype=torch.float64, device=dev)
-    # at theta_old: likelihood ratio == 1 exactly (same canonical summation order in rollout and update kernels)
+    # at theta_old: 64-wide nets -- likelihood ratio == 1 exactly (the FFMA loss kernel shares the rollout's summation
+    # order); 32-wide nets -- the loss pass runs its forward on the tensor cores (3xTF32): the rollout's mean to ~1e-7
     ops.loss_kl(L.LOSS_TRPO, th32, dd, 1e-6, b, out)
     o = out.cpu().numpy()
-    assert abs(o[0] + batch["adv"].mean()) < 1e-9 and abs(o[1]) < 1e-12 and abs(o[2]) < 1e-12
+    if hidden == 64:
+        assert abs(o[0] + batch["adv"].mean()) < 1e-9 and abs(o[1]) < 1e-12 and abs(o[2]) < 1e-12
+    else:
+        assert abs(o[0] + batch["adv"].mean()) < 1e-6 and abs(o[1]) < 1e-10 and abs(o[2]) < 1e-8
     # perturbed parameters: loss / KL / gradient against the float64 oracle
     rng = np.random.RandomState(9)
     th2 = theta + rng.randn(dims.P) * 0.02

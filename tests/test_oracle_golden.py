@@ -267,3 +267,64 @@ def test_cartpole_model_matches_reference_box2d_template():
     assert (e.lb[0], e.ub[0]) == tuple(r["ctrllimit"])
     assert e.bounds == (r["max_cart_pos"], r["max_cart_speed"], r["max_pole_angle"], r["max_pole_speed"])
     assert e.reset_range == r["reset_range"]
+
+
+def test_double_pendulum_model_matches_reference_box2d_template():
+    """oracle/envs.py::DoublePendulumEnv's constants re-derived from the reference's template and env class
+    (tests/golden/reference_double_pendulum_model.json <- models/double_pendulum.xml.mako, double_pendulum_env.py), plus
+    two physical sanity checks of the restated dynamics: energy is conserved without torque (to the integrator's order)
+    and the hanging equilibrium is a fixed point."""
+    import json
+    import os
+    from oracle import envs as E
+    r = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                    "reference_double_pendulum_model.json")))
+    e = E.DoublePendulumEnv
+    L = float(r["link_len_default"])
+    assert r["densities"] == [5.0, 5.0] and e.L == L
+    np.testing.assert_allclose(e.m, r["densities"][0] * r["link_width"] * L, rtol=1e-12)        # rectangle area x density
+    assert all(v.replace(" ", "") == "compute_rect_vertices([0,0],[0,-link_len],link_width/2)" for v in r["vertices_exprs"])
+    np.testing.assert_allclose(e.lc, L / 2, rtol=1e-12)                                         # COM half-way down the rod
+    np.testing.assert_allclose(e.I, e.m * (r["link_width"] ** 2 + L ** 2) / 12.0, rtol=1e-12)
+    assert [tuple(j) for j in r["joints"]] == [("revolute", "link_joint_1", "track", "link1", "0,0"),
+                                               ("revolute", "link_joint_2", "link1", "link2", "0,${-link_len}")]
+    assert r["controls"] == [["torque", "link_joint_2", e.lb[0], e.ub[0]]]
+    assert [tuple(s) for s in r["states"]] == [("apos", "link1", "sin"), ("apos", "link1", "cos"), ("avel", "link1", ""),
+                                               ("apos", "link2", "sin"), ("apos", "link2", "cos"), ("avel", "link2", "")]
+    assert e.dt_ == r["timestep"] and e.frame_skip == r["frame_skip_default"] and r["never_done"]
+    assert r["reset_stds"] == [0.1, 0.1, 0.01, 0.01]
+    assert r["tip_formula"] == ["cur_center_pos[0] - self.link_len*np.sin(cur_angle),",
+                                "cur_center_pos[1] - self.link_len*np.cos(cur_angle)"]
+    env = E.DoublePendulumEnv(np.float64)
+    raw = np.array([[3.0], [-2.0], [1.0], [0.5]])
+    s0 = env.reset(raw)
+    np.testing.assert_allclose(s0[:, 0], [0.3, -0.2, 0.01, 0.005], rtol=1e-12)
+    np.testing.assert_allclose(env.obs(s0)[:, 0], [np.sin(0.3), np.cos(0.3), 0.01, np.sin(-0.2), np.cos(-0.2), 0.005])
+
+    def energy(s):
+        th1, th2, w1, w2 = s[:, 0]
+        m, lc, Lk, I, g = env.m, env.lc, env.L, env.I, env.g
+        kin = 0.5 * (I + m * lc * lc + m * Lk * Lk) * w1 * w1 + 0.5 * (I + m * lc * lc) * w2 * w2 \
+            + m * Lk * lc * np.cos(th1 - th2) * w1 * w2
+        pot = -m * g * lc * np.cos(th1) - m * g * (Lk * np.cos(th1) + lc * np.cos(th2))
+        return kin + pot
+    # the equations of motion conserve the Lagrangian's energy: the drift of the semi-implicit Euler scheme over 4 s of
+    # free swinging shrinks with the step (first order), 100x from dt = 1e-2 to 1e-4
+    e_min = -env.m * env.g * (2 * env.lc + env.L)
+    drift = {}
+    for h, n in ((1e-2, 200), (1e-4, 20000)):
+        env.dt_, s = h, s0
+        for _ in range(n):
+            s, rew, done = env.step(s, np.zeros((1, 1)))
+        drift[h] = abs(energy(s) - energy(s0)) / (energy(s0) - e_min)
+        assert not done.any()
+    env.dt_ = E.DoublePendulumEnv.dt_
+    assert drift[1e-4] < 5e-3 and drift[1e-4] < 0.05 * drift[1e-2], drift
+    rest = np.zeros((4, 1))
+    s1, rew, _ = env.step(rest, np.zeros((1, 1)))
+    np.testing.assert_allclose(s1, 0.0, atol=1e-15)
+    np.testing.assert_allclose(rew, -4.0 * L)                                       # hanging tip (0,-2L) vs target (0,2L)
+    # tip formula of the reference (its x sign included): th1 = pi/2, th2 = pi/2 -> link2 origin (L, 0), tip (L - L, 0 - 0)
+    s2 = np.array([[np.pi / 2], [np.pi / 2], [0.0], [0.0]])
+    tx = L * np.sin(s2[0]) - L * np.sin(s2[1])
+    assert abs(tx[0]) < 1e-15
