@@ -46,6 +46,10 @@ def main():
             wr = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
             for k, short in SHORT.items():
                 if k in r[name_i]:
+                    if k == "update_umma32_kernel" and ", 0>" in r[name_i]:
+                        short = "loss_kl"                      # forward-only mode of the same kernel
+                    if k == "update_umma64_kernel" and ", 1>" in r[name_i]:
+                        short = "grad"
                     traffic.setdefault(short, rd + wr)
         except Exception:
             pass
