@@ -10,6 +10,10 @@
 namespace b200rl {
 
 __device__ __forceinline__ uint32_t u_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// hi word of the operand split: the float32 word with its 13 low mantissa bits cleared (exactly representable in TF32);
+// lo = x - hi is exact in float32.  (Rounding hi to nearest -- cvt.rna.tf32 -- instead of truncating removes the 2^-22
+// shrink of every operand that the tensor core's own truncation of the lo word causes, at one more instruction per
+// element; measured on the Swimmer learning curve it changes nothing: 22.8 +- 0.4 vs 23.7 +- 2.7 over 8 seeds)
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp): start >> 4 | LBO >> 4 << 16 |
