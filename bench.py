@@ -356,21 +356,12 @@ def main():
         hc = b.hcache(h, h)
         ops.grad(loss_kind, policy.theta32, dims, policy.min_std, b, g, None, hc)
         fvp_flops = (2.0 * O * h + 4.0 * h * h + 4.0 * h * A + 2.0 * (h * A + h * h) + F) * b.B
-        c64 = h == 32                      # the optimizer's default product: float64 chain where it is built
-        kern["fvp"] = dict(ms=timed(lambda: ops.fvp(policy.theta32, dims, policy.min_std, b, x, 1e-5, 1.0, Hx, hc,
-                                                    chain64=c64)),
-                           bytes=(4 * O + 8 * h) * b.B, flops=fvp_flops, per_iter=11,
-                           bound="fp64_issue" if c64 else "fp32_issue")
-        if c64:                            # the tcgen05 float32 product (fvp_chain="f32"), for comparison
-            kern["fvp_f32_tcgen05"] = dict(ms=timed(lambda: ops.fvp(policy.theta32, dims, policy.min_std, b, x, 1e-5, 1.0, Hx,
-                                                                    hc)),
-                                           bytes=(4 * O + 8 * h) * b.B, flops=fvp_flops, per_iter=0, bound="fp32_issue")
+        kern["fvp"] = dict(ms=timed(lambda: ops.fvp(policy.theta32, dims, policy.min_std, b, x, 1e-5, 1.0, Hx, hc)),
+                           bytes=(4 * O + 8 * h) * b.B, flops=fvp_flops, per_iter=11, bound="fp32_issue")
     for k, v in kern.items():
         v["GBps"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
         v["TFLOPs"] = v["flops"] / (v["ms"] * 1e-3) / 1e12
-        # fp64_issue: DFMA issues at half the FFMA rate on B200 -> half the measured FP32 peak
-        v["frac"] = (v["GBps"] / hbm_peak) if v["bound"] == "hbm" else \
-            (v["TFLOPs"] / (fp32_peak * (0.5 if v["bound"] == "fp64_issue" else 1.0)))
+        v["frac"] = (v["GBps"] / hbm_peak) if v["bound"] == "hbm" else (v["TFLOPs"] / fp32_peak)
         v["share_of_step"] = v["ms"] * v["per_iter"] / (ms_dev / args.steps)
     dom = max(kern, key=lambda k: kern[k]["ms"] * kern[k]["per_iter"])
     # dram bytes per launch from the ncu --set full capture of the shipped build (profiles/r02_traffic.json, written by

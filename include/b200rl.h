@@ -187,17 +187,6 @@ int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim
                const float* obs, const unsigned char* flags, const double* x, double scale, const double* count,
                double reg_coeff, double diag_scale, double* Hx_out, const float* h_cache, const int* tile_list,
                int n_list, double* ws, void* stream);
-/* The same product with everything that depends on the direction x through the network -- tangent forward and backward
- * chain of every sample -- evaluated in FLOAT64 (one thread per sample, DFMA; rllab_b200/csrc/update_fvp64.cu); the
- * sample-axis sums stay float32 products / float64 sums.  Requires (32,32) nets and h_cache.  The reference's product is
- * float64 (Theano floatX default); a float32 chain makes the computed operator asymmetric at 1e-7 |H|, which costs the
- * 10-iteration CG solve of conjugate_gradient_optimizer.py:253-258 about three iterations of depth.
- * This is the product the TRPO optimizer uses by default where it is built. */
-int b200rl_fvp_chain64(const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std, long long B,
-                       const float* obs, const unsigned char* flags, const double* x, double scale, const double* count,
-                       double reg_coeff, double diag_scale, double* Hx_out, const float* h_cache, const int* tile_list,
-                       int n_list, double* ws, void* stream);
-
 /* count_out[0] = number of unmasked samples inside the listed 128-sample tiles (tile_list NULL = whole batch). */
 int b200rl_count_valid(long long B, const unsigned char* flags, const int* tile_list, int n_list, double* count_out,
                        double* ws, void* stream);

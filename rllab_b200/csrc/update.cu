@@ -184,10 +184,10 @@ int b200rl_grad(int loss_kind, const float* params_f32, int obs_dim, int h1, int
   return launch_finalize_update(f, st);
 }
 
-static int fvp_impl(bool chain64, const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std,
-                    long long B, const float* obs, const unsigned char* flags, const double* x, double scale,
-                    const double* count, double reg_coeff, double diag_scale, double* Hx_out, const float* h_cache,
-                    const int* tile_list, int n_list, double* ws, void* stream) {
+int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std, long long B,
+               const float* obs, const unsigned char* flags, const double* x, double scale, const double* count,
+               double reg_coeff, double diag_scale, double* Hx_out, const float* h_cache, const int* tile_list,
+               int n_list, double* ws, void* stream) {
   B200RL_REQUIRE(params_f32 && obs && x && Hx_out && ws && B > 0, "fvp: bad arguments");
   B200RL_REQUIRE(h1 == h2 && (h1 == 32 || h1 == 64), "fvp: hidden sizes must be (32,32) or (64,64)");
   B200RL_REQUIRE(tile_list == nullptr || n_list > 0, "fvp: empty tile list");
@@ -196,12 +196,6 @@ static int fvp_impl(bool chain64, const float* params_f32, int obs_dim, int h1, 
   fill_args(a, params_f32, min_std, B, obs, nullptr, nullptr, nullptr, nullptr, B200RL_LOSS_TRPO, flags, ws);
   a.xvec = x; a.h_cache = const_cast<float*>(h_cache); a.tile_list = tile_list; a.n_list = n_list;
   int grid = 0, P = 0, ols = 0;
-  if (chain64) {
-    B200RL_REQUIRE(h1 == 32 && h_cache != nullptr,
-                   "fvp_chain64: built for (32,32) nets with the activation cache of the gradient pass");
-    int rc = update_fvp64_launch(obs_dim, act_dim, a, &grid, &P, &ols, st);
-    if (rc) return rc;
-  } else {
   // 64-wide nets with cached activations: tcgen05 kernel (update_umma.cu); without a cache the FP32 tiled-GEMM kernel
   // 32-wide nets with cached activations: tcgen05 kernel (update_umma32.cu); without a cache the FP32 tile kernel
 #ifdef B200RL_AB_TILE32
@@ -213,29 +207,12 @@ static int fvp_impl(bool chain64, const float* params_f32, int obs_dim, int h1, 
            : (h_cache != nullptr) ? update_umma64_launch(MODE_FVP, obs_dim, act_dim, a, &grid, &P, &ols, st)
                                   : update_gemm_launch(MODE_FVP, obs_dim, h1, act_dim, a, &grid, &P, &ols, st);
   if (rc) return rc;
-  }
   FinArgs f{};
   f.partial = ws; f.nblocks = grid; f.K = P; f.vec_out = Hx_out; f.tri_out = nullptr;
   f.scale = scale; f.count = count; f.post = FIN_FVP; f.ols = ols; f.A = act_dim;
   f.params32 = params_f32; f.log_min_std = (double)a.log_min_std; f.x = x; f.reg = reg_coeff; f.diag_scale = diag_scale;
   if (peer_fused()) f.peer = peer_next();
   return launch_finalize_update(f, st);
-}
-
-int b200rl_fvp(const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std, long long B,
-               const float* obs, const unsigned char* flags, const double* x, double scale, const double* count,
-               double reg_coeff, double diag_scale, double* Hx_out, const float* h_cache, const int* tile_list,
-               int n_list, double* ws, void* stream) {
-  return fvp_impl(false, params_f32, obs_dim, h1, h2, act_dim, min_std, B, obs, flags, x, scale, count, reg_coeff, diag_scale,
-                  Hx_out, h_cache, tile_list, n_list, ws, stream);
-}
-
-int b200rl_fvp_chain64(const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std, long long B,
-                       const float* obs, const unsigned char* flags, const double* x, double scale, const double* count,
-                       double reg_coeff, double diag_scale, double* Hx_out, const float* h_cache, const int* tile_list,
-                       int n_list, double* ws, void* stream) {
-  return fvp_impl(true, params_f32, obs_dim, h1, h2, act_dim, min_std, B, obs, flags, x, scale, count, reg_coeff, diag_scale,
-                  Hx_out, h_cache, tile_list, n_list, ws, stream);
 }
 
 int b200rl_count_valid(long long B, const unsigned char* flags, const int* tile_list, int n_list, double* count_out,

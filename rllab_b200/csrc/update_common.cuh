@@ -58,7 +58,4 @@ int update_umma32_launch(int mode, int obs_dim, int act_dim, const UpdArgs& a, i
                          cudaStream_t st);
 
 
-// 32-wide nets, Fisher-vector product with cached activations and the per-sample chain in float64 (update_fvp64.cu)
-int update_fvp64_launch(int obs_dim, int act_dim, const UpdArgs& a, int* grid_out, int* P_out, int* ols_out, cudaStream_t st);
-
 }  // namespace b200rl

@@ -216,7 +216,7 @@ def grad(loss_kind, params32, dims, min_std, batch, g_out, loss_out=None, h_cach
 
 
 def fvp(params32, dims, min_std, batch, x, reg_coeff, diag_scale, Hx_out, h_cache=None, tile_list=None, count=None,
-        fuse=False, chain64=False):
+        fuse=False):
     """tile_list (int32 device tensor) + count (float64 device scalar: valid samples in those tiles over all ranks):
     the sub-sampled product of subsample_factor < 1."""
     O, h1, h2, A = dims
@@ -226,7 +226,7 @@ def fvp(params32, dims, min_std, batch, x, reg_coeff, diag_scale, Hx_out, h_cach
         scale, cnt = 1.0, L.ptr(count)
     _chk(params32, F32, "params32"), _chk(x, F64, "x"), _chk(Hx_out, F64, "Hx_out", x.numel())
     with _Fused(fuse):
-        L.call("b200rl_fvp_chain64" if chain64 else "b200rl_fvp", L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs), fl, L.ptr(x), scale,
+        L.call("b200rl_fvp", L.ptr(params32), O, h1, h2, A, float(min_std or 0.0), b.B, L.ptr(b.obs), fl, L.ptr(x), scale,
                cnt, float(reg_coeff), float(diag_scale), L.ptr(Hx_out), L.ptr(h_cache), L.ptr(tile_list),
                0 if tile_list is None else int(tile_list.numel()), L.ptr(workspace(b.device)), _stream())
 

@@ -10,12 +10,11 @@ line-search trial.
 
 Hessian-vector products (hvp_approach=):
   None / PerlmutterHvp()      exact product of the Hessian of mean KL = Gauss-Newton / Fisher product (:22-55).
-                              fvp_chain="auto" (default): b200rl_fvp_chain64 where it is built ((32,32) nets) -- the
-                              per-sample tangent / backward chain in float64, as the reference's float64 product; the CG
-                              solve needs that (a float32 chain costs it ~3 of its 10 iterations of depth: Swimmer
-                              AverageReturn at iteration 40, 8 seeds: 23.7 +- 2.7 vs 30.5 +- 1.5, oracle 31.6) -- else the
-                              tcgen05 float32 kernel; "f32": always b200rl_fvp (tcgen05, 1.5x faster); precision="f64":
-                              every pass on the float64 parity kernels
+                              The float32 b200rl_fvp kernels (precision="f32", tcgen05) or the float64 parity kernels
+                              (precision="f64").  NOTE: the reference's product is float64; on ill-conditioned Fisher systems
+                              the float32 product costs the 10-iteration CG solve about three iterations of depth, which
+                              shows in the learning speed of Swimmer -- raise cg_iters or use
+                              precision="f64" where that matters more than speed.
   FiniteDifferenceHvp(...)    (:58-115) two gradient passes of mean KL at theta +- eps x; eps = base_eps / |theta| ~ 1e-9
                               is below float32 resolution, so this approach always runs the float64 kernels
 subsample_factor < 1 (:235-245): the products use a random subset of the batch, drawn with np.random.choice like the
@@ -50,15 +49,13 @@ class FiniteDifferenceHvp(object):
 class ConjugateGradientOptimizer(object):
     def __init__(self, cg_iters=10, reg_coeff=1e-5, subsample_factor=1., backtrack_ratio=0.8, max_backtracks=15,
                  accept_violation=False, hvp_approach=None, num_slices=1, residual_tol=1e-10,
-                 use_activation_cache=True, precision="f32", cg_direction_f32=False, fvp_chain="auto"):
+                 use_activation_cache=True, precision="f32", cg_direction_f32=False):
         if not (0.0 < subsample_factor <= 1.0):
             raise ValueError("subsample_factor must be in (0, 1]")
         if hvp_approach is not None and not isinstance(hvp_approach, (PerlmutterHvp, FiniteDifferenceHvp)):
             raise TypeError("hvp_approach must be PerlmutterHvp() or FiniteDifferenceHvp()")
         if precision not in ("f32", "f64"):
             raise ValueError("precision must be 'f32' (fast path) or 'f64' (parity mode)")
-        if fvp_chain not in ("auto", "f64", "f32"):
-            raise ValueError("fvp_chain must be 'auto', 'f64' or 'f32'")
         self._cg_iters = cg_iters
         self._reg_coeff = reg_coeff
         self._subsample_factor = subsample_factor
@@ -80,7 +77,6 @@ class ConjugateGradientOptimizer(object):
         self._f64 = precision == "f64"
         self._use_hcache = use_activation_cache and not self._f64
         self._p_f32 = bool(cg_direction_f32) and not self._f64
-        self._fvp_chain = fvp_chain
         self.last_info = {}
 
     def __getstate__(self):
@@ -208,19 +204,13 @@ class ConjugateGradientOptimizer(object):
                 out.add_(vec, alpha=self._reg_coeff)
             return Hx
 
-        # float64 chain (b200rl_fvp_chain64): built for (32,32) nets, needs the activation cache of the gradient pass
-        chain64_ok = pol.h1 == 32 and pol.h2 == 32 and hcache is not None
-        if self._fvp_chain == "f64" and not chain64_ok and not self._f64:
-            raise NotImplementedError("fvp_chain='f64' needs a (32,32) policy and use_activation_cache=True")
-        chain64 = chain64_ok and self._fvp_chain in ("auto", "f64")
-
         def Hx(vec, out):
             if self._f64:
                 ops.update_f64(2, self._loss_kind, pol.theta64, pol.dims, pol.min_std, batch, vec, self._reg_coeff,
                                1.0 / world, out, None, fuse=self._fuse())
             else:
                 ops.fvp(pol.theta32, pol.dims, pol.min_std, batch, vec, self._reg_coeff, 1.0 / world, out, hcache,
-                        tiles, b["cnt"] if tiles is not None else None, fuse=self._fuse(), chain64=chain64)
+                        tiles, b["cnt"] if tiles is not None else None, fuse=self._fuse())
             self._after_pass(out)
         return Hx
 
