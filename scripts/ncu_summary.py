@@ -48,6 +48,8 @@ def main():
                 if k in r[name_i]:
                     if k == "update_umma32_kernel" and ", 0>" in r[name_i]:
                         short = "loss_kl"                      # forward-only mode of the same kernel
+                    if k == "update_umma32_kernel" and ", 2>" in r[name_i]:
+                        short = "fvp"
                     if k == "update_umma64_kernel" and ", 1>" in r[name_i]:
                         short = "grad"
                     traffic.setdefault(short, rd + wr)

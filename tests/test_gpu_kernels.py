@@ -535,3 +535,31 @@ def test_f64_parity_kernels_match_oracle(dev, env_name, hidden):
     ops.update_f64(2, L.LOSS_TRPO, th0, dd, 1e-6, b, xd, 1e-5, 1.0, Hx, None)
     ref_Hx = P.fvp(theta, batch, x, dims, 1e-5)
     np.testing.assert_allclose(Hx.cpu().numpy(), ref_Hx, rtol=1e-8, atol=1e-12 * np.abs(ref_Hx).max())
+
+
+@pytest.mark.parametrize("O,A", [(6, 1), (13, 2), (20, 3), (4, 1)])
+def test_lfb_gram_matches_numpy_on_synthetic_batches(dev, O, A):
+    """LinearFeatureBaseline normal equations (linear_feature_baseline.py:19-37) on a synthetic batch for every compiled
+    obs_dim: the register-tiled kernel (obs_dim 6 / 13 / 20), the register-triangle kernel (<= 4), ragged sizes (B not a
+    multiple of the 128-sample tile or of 4), masked samples, observations beyond the +-10 clip."""
+    ops, L = _ops(), _L()
+    for N, T in ((200, 37), (128, 64), (333, 5)):
+        rng = np.random.RandomState(O * 100 + N)
+        b = ops.LaneBatch(O, A, N, T, dev)
+        obs = (rng.randn(O, T, N) * 6.0).astype(np.float32)
+        ts = rng.randint(0, 500, size=(T, N)).astype(np.uint16)
+        ret = (rng.randn(T, N) * 30.0).astype(np.float32)
+        fl = np.where(rng.rand(T, N) < 0.2, L.FLAG_MASKED, 0).astype(np.uint8)
+        b.obs.copy_(torch.tensor(obs)), b.ret.copy_(torch.tensor(ret)), b.flags.copy_(torch.tensor(fl))
+        b.tstep.copy_(torch.tensor(ts.view(np.int16)).view(torch.uint16))
+        b.masked = True
+        d1 = 2 * O + 5
+        gram = torch.empty((d1 * (d1 + 1) // 2,), dtype=torch.float64, device=dev)
+        ops.lfb_gram(b, gram)
+        keep = (fl.reshape(-1) & L.FLAG_MASKED) == 0
+        o = np.clip(obs.reshape(O, -1).astype(np.float64), -10, 10)
+        al = ts.reshape(-1).astype(np.float64) / 100.0
+        F = np.concatenate([o, o ** 2, al[None], al[None] ** 2, al[None] ** 3, np.ones((1, al.size)),
+                            ret.reshape(1, -1).astype(np.float64)], axis=0)[:, keep]
+        G = (F @ F.T)[np.triu_indices(d1)]
+        np.testing.assert_allclose(gram.cpu().numpy(), G, rtol=2e-5, atol=2e-5 * np.abs(G).max())
