@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(V_THREADS, (Umma32<N, MODE>::MINB)) update_umm
         split_gemm(SM::cACC_B, SM::cOP_HI, SM::cOP_LO, dV1T_hi, dV1T_lo, 4, false);            // H1 V1
       u_commit(&bars[0]);
     }
-    // GRAD / LOSS: the remaining per-sample inputs, requested while the first GEMM runs
+    // GRAD / LOSS: the remaining per-sample inputs, requested while the first GEMM runs (prefetching them and the
+    // observations one tile ahead in registers was measured: no gain, 2.05 -> 2.07 ms)
     float act[A], om[A], adv_s = 0.f;
     if constexpr (MODE != MODE_FVP) {
 #pragma unroll
@@ -381,6 +382,7 @@ __global__ void __launch_bounds__(V_THREADS, (Umma32<N, MODE>::MINB)) update_umm
         split_gemm(SM::cACC_A, SM::cOP_HI, SM::cOP_LO, dW1_hi, dW1_lo, 4, false);               // D2 W1^T
         u_commit(&bars[2]);
       }
+      // (an L2 prefetch of the next tile's rows from here, as update_umma.cu does, was measured on Swimmer: 1.73 -> 1.77 ms)
       // ================= Gram part A behind the last GEMM: dW1 = H1^T D2, dWout, db1, dbout, dlog_std (tile_gram.cuh)
       gram.accumulate_a(stage, tid);
       __syncthreads();                       // every thread is done with the H2 rows: D1 may overwrite them
