@@ -271,6 +271,7 @@ def main():
         comm.dist.all_gather(gathered, theta_dev)
         replicas_identical = all(bool(torch.equal(gathered[0], g)) for g in gathered)
         assert replicas_identical, "policy parameters differ across ranks"
+        assert comm.peer_timeouts() == 0, "a peer-memory collective timed out"
 
     # ---- rank-count invariance on a small problem: the sharded run of this job reproduces, on every rank, the
     # single-process run of the same total lanes (Philox is keyed by the GLOBAL lane; reductions are float64, rank order)

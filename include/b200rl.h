@@ -253,6 +253,9 @@ int b200rl_peer_allreduce_mixed(double* t, long long n, long long n_sum, void* s
  * reduced over ALL ranks -- the exchange is fused into the finalize kernel of the pass (one launch: fold the per-block
  * partials, push into the peers' windows, fold over ranks).  Every rank must issue the same sequence of calls. */
 int b200rl_peer_fuse_updates(int enable);
+/* Number of collectives of this rank that gave up waiting (30 s) for a peer; their results were poisoned with NaN.
+ * Synchronising device->host read: call it at the end of a job, not inside the iteration. */
+int b200rl_peer_timeouts(unsigned int* count_out_host);
 
 /* (T,N)-planar lane layout <-> the reference's sample-major (B, dim) float64 wire format
  * (samples_data["observations"] etc., rllab/sampler/base.py:74-104): dst[(t*N+n)*dim + k] = src[k][t][n]. */

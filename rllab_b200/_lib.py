@@ -68,6 +68,7 @@ SIGNATURES = {
     "b200rl_peer_bind": (c_int, [_P, c_int, c_int, _LL]),
     "b200rl_peer_allreduce_mixed": (c_int, [_P, _LL, _LL, _P]),
     "b200rl_peer_fuse_updates": (c_int, [c_int]),
+    "b200rl_peer_timeouts": (c_int, [POINTER(c_uint)]),
     "b200rl_reduce_ranks": (c_int, [_P, c_int, _LL, _LL, _P, _P]),
     "b200rl_planes_to_rows_f64": (c_int, [c_int, _LL, _P, _P, _P]),
 }

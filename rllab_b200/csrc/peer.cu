@@ -111,6 +111,15 @@ int b200rl_peer_fuse_updates(int enable) {
   return 0;
 }
 
+int b200rl_peer_timeouts(unsigned int* count_out_host) {
+  B200RL_REQUIRE(count_out_host != nullptr, "peer_timeouts: bad arguments");
+  *count_out_host = 0;
+  if (!peer_bound()) return 0;
+  B200RL_CUDA_CHECK(cudaMemcpy(count_out_host, g_peer.win[g_peer.rank] + PEER_FLAGS_BYTES + 8, sizeof(unsigned int),
+                               cudaMemcpyDeviceToHost));       // synchronising: call it outside the hot path
+  return 0;
+}
+
 int b200rl_peer_allreduce_mixed(double* t, long long n, long long n_sum, void* stream) {
   B200RL_REQUIRE(peer_bound(), "peer_allreduce_mixed: no communicator bound");
   B200RL_REQUIRE(t && n >= 1 && n <= g_peer.n_cap && n_sum >= 0 && n_sum <= n, "peer_allreduce_mixed: bad arguments");

@@ -31,6 +31,11 @@ __device__ __forceinline__ unsigned long long* peer_flag(unsigned char* win, int
 __device__ __forceinline__ unsigned int* peer_done_counter(unsigned char* win) {
   return reinterpret_cast<unsigned int*>(win + PEER_FLAGS_BYTES);
 }
+// number of collectives of this rank that gave up waiting for a peer (their results were poisoned with NaN); the host
+// reads it back through b200rl_peer_timeouts()
+__device__ __forceinline__ unsigned int* peer_timeout_counter(unsigned char* win) {
+  return reinterpret_cast<unsigned int*>(win + PEER_FLAGS_BYTES + 8);
+}
 __device__ __forceinline__ double* peer_slot(const PeerArgs& p, int win_rank, int par, int src_rank) {
   return reinterpret_cast<double*>(p.win[win_rank] + PEER_SLOT_OFFSET) + ((size_t)par * p.world + src_rank) * p.n_cap;
 }
@@ -59,7 +64,10 @@ __device__ __forceinline__ bool peer_wait(const PeerArgs& p, int src) {
   const unsigned long long* f = peer_flag(p.win[p.rank], (int)(p.seq & 1ull), src);
   const unsigned long long t0 = peer_globaltimer();
   while (peer_ld_acquire(f) < p.seq) {
-    if (peer_globaltimer() - t0 > 30000000000ull) return false;
+    if (peer_globaltimer() - t0 > 30000000000ull) {
+      atomicAdd(peer_timeout_counter(p.win[p.rank]), 1u);
+      return false;
+    }
   }
   return true;
 }

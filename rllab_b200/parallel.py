@@ -88,6 +88,15 @@ class Comm(object):
         torch.cuda.synchronize()
         self.dist.barrier()
 
+    def peer_timeouts(self):
+        """Collectives of this rank that gave up waiting for a peer (synchronising read; 0 without the peer transport)."""
+        if not self.peer:
+            return 0
+        from . import _lib as L
+        n = ctypes.c_uint(0)
+        L.call("b200rl_peer_timeouts", ctypes.byref(n))
+        return int(n.value)
+
     @property
     def fuse(self):
         """True when the update passes should reduce over ranks inside their own finalize kernel."""
@@ -159,15 +168,21 @@ class Comm(object):
             from . import _lib as L
             torch.cuda.synchronize()
             self.dist.barrier()                      # nobody still pushes into a window that is about to go away
+            n_timeouts = self.peer_timeouts()
             L.call("b200rl_peer_bind", None, 0, 0, 0)
             own, opened = self._windows
             for ptr in opened.values():
                 L.call("b200rl_peer_window_close", ptr)
             L.call("b200rl_peer_window_destroy", own)
             self.peer, self._windows = False, None
+        else:
+            n_timeouts = 0
         if self.active and self._owns_group and self.dist.is_initialized():
             self.dist.destroy_process_group()
             self._owns_group = False
+        if n_timeouts:
+            raise RuntimeError("%d peer-memory collective(s) of rank %d timed out waiting for a peer; their results were "
+                               "NaN" % (n_timeouts, self.rank))
 
     def shard(self, n_total):
         """Contiguous lane block of this rank: lane i -> GPU floor(i*G/N)."""
