@@ -159,7 +159,12 @@ int b200rl_lfb_solve(int obs_dim, const double* gram, double reg_coeff, double* 
  * Common to the update passes: `flags` ([B] or NULL) -- samples carrying B200RL_FLAG_MASKED are skipped; `count` (device
  * pointer or NULL) -- the sums are additionally divided by *count, the all-reduced number of valid samples
  * (sums_out[2] of b200rl_process_samples): pass scale = 1 and count = &sums[2] for the mean over the valid samples of
- * all ranks without reading the count back to the host. */
+ * all ranks without reading the count back to the host.
+ * Arithmetic of the three update passes (loss_kl, grad, fvp): float32 per sample, float32 sums inside one 128-sample
+ * tile, float64 above.  (32,32) nets: every pass runs its dense layers on the tcgen05 tensor cores with the three-pass
+ * TF32 split (float32-grade, 4e-7 of the output scale); (64,64) nets: grad and fvp (with h_cache) likewise, loss_kl on
+ * the FP32 pipe in the rollout's summation order (ratio exactly 1 at theta_old).  While b200rl_peer_fuse_updates(1) is in
+ * effect the outputs are reduced over all ranks of the bound peer communicator inside the pass. */
 int b200rl_loss_kl(int loss_kind, const float* params_f32, int obs_dim, int h1, int h2, int act_dim, float min_std,
                    long long B, const float* obs, const float* act, const float* adv, const float* old_mean,
                    const float* old_log_std, const unsigned char* flags, double scale, const double* count, double* out,
