@@ -66,7 +66,10 @@ struct Umma32 {
                        R = (MODE == MODE_LOSS) ? 0 : rDL + A;
   static constexpr int o_red = ((o_stage + R * V_LD * 4 + 15) / 16) * 16;   // 3 x 32 doubles of reduction scratch
   static constexpr int o_bar = o_red + 3 * 32 * 8;
-  static constexpr size_t bytes = (size_t)o_bar + 64;
+  // the forward-only pass needs 11 KB; it asks for enough that a fifth CTA cannot become resident on an SM (registers would
+  // allow it): every resident CTA must be able to allocate its 128 TMEM columns, and there are 512
+  static constexpr size_t need = (size_t)o_bar + 64, floor4 = (228 * 1024) / 5 + 1;
+  static constexpr size_t bytes = (MODE == MODE_LOSS && need < floor4) ? floor4 : need;
   static_assert(MODE == MODE_LOSS || 2 * 64 * 16 * 8 <= R * V_LD * 4, "stage region must hold the K-half combine scratch");
   static_assert(bytes <= 232448, "does not fit the 227 KB of shared memory");
   // resident CTAs per SM: shared memory (228 KB, 1 KB reserved per CTA), TMEM (512 columns), registers (64 K / 128 threads)
