@@ -1,10 +1,11 @@
-// Phase B of the 32-wide update kernels (update_tile.cu: FP32 layer chain; update_umma32.cu: tcgen05 layer chain): the
+// Gram phase of the 32-wide update kernels (update_tile.cu: FP32 layer chain; update_umma32.cu: tcgen05 layer chain): the
 // weight gradients as Gram products over one 128-sample tile staged feature-major in shared memory,
 //     dW0 = X^T D1, db0 = 1^T D1, dW1 = H1^T D2, db1 = 1^T D2, dWout = H2^T DM, dbout = 1^T DM, dlog_std = 1^T DL,
 // accumulated by the 128 threads of the CTA: dW1 (32 x 32 outputs, the bulk) in 4x4 register tiles, rows interleaved by 8
-// so that every LDS.128 of a warp is conflict-free, split in two K-halves over the threads; the small outputs by warps
-// 0 / 1 / 2.  Per-tile float32 partial products are folded into float64 register accumulators that live across the
-// persistent tile loop; write() combines the K-halves through shared memory and stores the block's float64 partial vector.
+// so that every LDS.128 of a warp is conflict-free, split in two K-halves over the threads; the small outputs spread over
+// the four warps (see TileGram).  Per-tile float32 partial products are folded into float64 register accumulators that
+// live across the persistent tile loop; write() combines the K-halves through shared memory and stores the block's float64
+// partial vector.
 #pragma once
 #include "update_common.cuh"
 
